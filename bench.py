@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (contract in the task brief / DESIGN.md §Measurement).
+
+A "step" is one pass of the hot path over one batch of synthetic input: stage-1 synthesis of
+`utts_per_gpu` utterances (BASELINE.json configs[1]: T=48 prompt, 750 new tokens = 5.0 s of audio,
+top_p 0.95, guidance 3.0, temperature 1.0, bf16 weights + bf16 KV cache) on every GPU.
+
+  value  : whole-job stage-1 tokens/s with inputs already resident in HBM (prefill + decode on device)
+  e2e    : same metric through the reference-facing plugin call mvb_s1_generate with HOST buffers
+           (prompt/speaker host->device, tokens device->host inside the timed region)
+  roofline: the decode step (one CUDA graph replay), algorithmic bytes / CUDA-event time vs measured HBM peak
+  cpu_baseline: the oracle port of the reference's CPU path, timed on this box's host cores (bounded sample)
+
+`--impl reference` times the reference's CPU implementation (oracle port; the Python reference cannot travel
+to the GPU box) on the same metric; under torchrun only rank 0 runs it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "metavoice-src_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+T_PROMPT, N_NEW = 48, 750
+SAMPLING = dict(guidance_scale=3.0, temperature=1.0, top_p=0.95)
+W_BYTES = 2_476_953_600            # stage-1 weight bytes streamed per decode step
+KV_BYTES_PER_POS = 393_216         # K+V bytes per cached position per utterance (2 CFG rows, 24 layers, bf16)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        try:
+            j = json.load(open(path))
+            return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_engine(device, utts, rank, world):
+    from mvb200 import synth
+    from mvb200.fast_model import ModelArgs, Transformer, pack_arena
+    d = synth.FULL
+    cfg = ModelArgs.from_name("metavoice-1B")
+    t0 = time.time()
+    if rank == 0:
+        arena, offsets = pack_arena(synth.stage1_state_dict(d, 0), d.n_layer)
+        arena = arena.to(device)
+    else:
+        arena, offsets = None, None
+    bcast_ms = None
+    if world > 1:
+        import torch.distributed as dist
+        meta = [offsets, None if arena is None else arena.numel()]
+        dist.broadcast_object_list(meta, src=0)
+        offsets, nbytes = meta
+        if arena is None:
+            arena = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        torch.cuda.synchronize(device); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); dist.broadcast(arena, src=0); e1.record()   # the ONE collective of the path: NCCL over NVLink
+        torch.cuda.synchronize(device)
+        bcast_ms = e0.elapsed_time(e1)
+    model = Transformer(cfg, arena, offsets, device=device)
+    model.setup_spk_cond_mask()
+    model.setup_caches(2 * utts, cfg.block_size, kv_dtype="bf16")
+    return model, time.time() - t0, bcast_ms
+
+
+def resident_pass(model, d_idx, d_spk, utts, seed):
+    """Prefill + decode with inputs already in HBM; returns tokens generated (device time is measured by the caller)."""
+    import ctypes as C
+    from mvb200 import _lib
+    lib, h, st = model._lib, model.handle, model._stream()
+    for u in range(utts):
+        sp = _lib.Sampling(SAMPLING["guidance_scale"], SAMPLING["temperature"], SAMPLING["top_p"], 0, 9999, seed + u)
+        _lib.check(lib.mvb_s1_set_speaker(h, u, d_spk[u].data_ptr(), st))
+        _lib.check(lib.mvb_s1_begin(h, u, -1, 0, C.byref(sp), None, None, st))
+        _lib.check(lib.mvb_s1_forward(h, u, d_idx[u].data_ptr(), T_PROMPT, 0, None, 0, st))
+    # decode() = N_NEW x (body, sampler).  Its first body replays the last prefill position (idempotent cache
+    # write) so that the first token is sampled from the prefill logits exactly as generate() does (utils:211).
+    _lib.check(lib.mvb_s1_decode(h, utts, N_NEW, st))
+    return utts * N_NEW
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mvb200", choices=["mvb200", "reference"])
+    ap.add_argument("--utts-per-gpu", type=int, default=1)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if a.impl == "reference":
+        if rank == 0:
+            print(json.dumps(reference_arm(a)))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    utts = a.utts_per_gpu
+    model, build_s, bcast_ms = build_engine(device, utts, rank, world)
+    from mvb200 import synth, fast_inference_utils as U
+
+    prompts = [synth.synthetic_prompt(T_PROMPT, seed=7 + rank * 64 + u) for u in range(utts)]
+    spk = torch.cat([synth.synthetic_speaker(seed=11 + rank * 64 + u) for u in range(utts)])
+    d_idx = [p.view(1, -1).repeat(2, 1).to(device).contiguous() for p in prompts]
+    d_spk = [spk[u].to(device).contiguous() for u in range(utts)]
+    h_spk_pinned = spk.pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    # ---- HBM-resident value ------------------------------------------------------------------
+    for w in range(a.warmup):
+        resident_pass(model, d_idx, d_spk, utts, 1000 + w)
+    barrier()
+    lc0 = model._lib.mvb_s1_launch_count(model.handle)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        toks = 0
+        for k in range(a.steps):
+            toks += resident_pass(model, d_idx, d_spk, utts, 2000 + k)
+        e1.record()
+        barrier()
+    launches = model._lib.mvb_s1_launch_count(model.handle) - lc0
+    ms = e0.elapsed_time(e1)
+
+    # ---- decode-step roofline: CUDA events around graph replays at a fixed context length -----
+    import ctypes as C
+    reps = 200
+    model._lib.mvb_s1_decode(model.handle, utts, 8, model._stream())
+    torch.cuda.synchronize(device)
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # rewind to mid-utterance so the KV term is representative (L ~ T + N_NEW/2)
+    resident_pass(model, d_idx, d_spk, utts, 1)  # leaves pos = T+N_NEW
+    from mvb200 import _lib
+    for u in range(utts):
+        sp = _lib.Sampling(3.0, 1.0, 0.95, 0, 9999, 5)
+        _lib.check(model._lib.mvb_s1_begin(model.handle, u, 100, T_PROMPT + N_NEW // 2 - reps // 2, C.byref(sp), None, None,
+                                           model._stream()))
+    torch.cuda.synchronize(device)
+    r0.record()
+    _lib.check(model._lib.mvb_s1_decode(model.handle, utts, reps, model._stream()))
+    r1.record()
+    torch.cuda.synchronize(device)
+    step_ms = r0.elapsed_time(r1) / reps
+    L_mid = T_PROMPT + N_NEW // 2
+    step_bytes = W_BYTES + utts * (KV_BYTES_PER_POS * L_mid + KV_BYTES_PER_POS)
+    peak, peak_src = measured_peaks()
+    achieved = step_bytes / (step_ms * 1e-3) / 1e9
+
+    # ---- e2e through the host-buffer plugin call ---------------------------------------------
+    for w in range(max(1, a.warmup // 2)):
+        U.generate_batch(model, prompts, h_spk_pinned, max_new_tokens=N_NEW, end_of_audio_token=9999, seed=3000 + w, **SAMPLING)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_toks = 0
+    for k in range(a.steps):
+        out = U.generate_batch(model, prompts, h_spk_pinned, max_new_tokens=N_NEW, end_of_audio_token=9999, seed=4000 + k,
+                               **SAMPLING)
+        e2e_toks += sum(len(o) for o in out)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = [float(x) for x in times.cpu()]
+    if rank != 0:
+        return
+    total_toks = toks * world
+    value = total_toks / (ms_max * 1e-3)
+    line = {
+        "metric": "stage1_tok_per_s", "value": round(value, 2), "unit": "tokens/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": round(ms_max / a.steps, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16 weights+KV, fp32 accumulate", "data": "synthetic (seeded random-init checkpoint in the reference layout)",
+        "audio_sec_per_s_stage1": round(value / 150.0, 3),
+        "config": {"workload": "BASELINE configs[1] stage-1: 1.2B causal LM, T=48 prompt, 750 new tokens (5.0 s audio), "
+                               "top_p=0.95 guidance=3.0 temperature=1.0, CFG pair per utterance",
+                   "utts_per_gpu": utts, "parallelism": f"replicas x{world}, utterances sharded, weights NCCL-broadcast at init",
+                   "l2": "not flushed: 2.48 GB of weights are streamed every token (>> 126 MB L2)",
+                   "stage2_vocoder_in_timed_region": False},
+        "e2e": {"value": round(e2e_toks * world / (e2e_ms_max * 1e-3), 2), "unit": "tokens/s",
+                "h2d_bytes_per_step": int(utts * (T_PROMPT * 4 * 2 + 256 * 4 + 32)), "d2h_bytes_per_step": int(utts * (N_NEW * 4 + 8))},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "decode step (one CUDA-graph replay: 24x{qkv,attn,wo,w13,w2} + head) + sampler",
+                     "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                     "frac": round(achieved / peak, 4), "traffic": None, "bytes_per_launch": int(step_bytes),
+                     "ms_per_launch": round(step_ms, 4), "context_len": L_mid},
+        "clocks": clk.summary(),
+        "init": {"build_s": round(build_s, 2), "nccl_broadcast_ms": bcast_ms},
+    }
+    if not a.skip_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line))
+
+
+def _oracle_stage1(dtype):
+    from mvb200 import synth
+    from oracle import stage1_port as P
+    d = synth.FULL
+    m = P.Stage1Oracle(synth.stage1_state_dict(d, 0), d.n_head, d.norm_eps, dtype, faithful_full_cache=True)
+    m.setup_caches()
+    return m
+
+
+def cpu_baseline(n_decode=24, model=None):
+    """Oracle port of the reference's CPU path (bf16, its production dtype), all host threads; bounded sample:
+    prefill of the T=48 prompt + n_decode decode steps of the same workload."""
+    from mvb200 import synth
+    from oracle import stage1_port as P
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = model or _oracle_stage1(torch.bfloat16)
+    prompt, spk = synth.synthetic_prompt(T_PROMPT), synth.synthetic_speaker()
+    torch.manual_seed(1337)
+    t0 = time.perf_counter()
+    y = P.generate(m, prompt, spk.to(torch.bfloat16), max_new_tokens=n_decode + 1, end_of_audio_token=9999, **SAMPLING)
+    dt = time.perf_counter() - t0
+    n = y.numel() - prompt.numel()
+    return {"value": round(n / dt, 3), "unit": "tokens/s", "cores": cores, "kind": "port",
+            "sample": f"prefill T={T_PROMPT} + {n_decode} decode steps of the 750-token workload, bf16, torch CPU ({cores} threads)"}
+
+
+def reference_arm(a):
+    cores = os.cpu_count() or 1
+    m = _oracle_stage1(torch.bfloat16)
+    for _ in range(min(a.warmup, 1)):
+        cpu_baseline(4, m)
+    t0 = time.perf_counter()
+    vals = [cpu_baseline(16, m) for _ in range(a.steps)]
+    dt = time.perf_counter() - t0
+    v = sum(x["value"] for x in vals) / len(vals)
+    cb = dict(vals[-1]); cb["value"] = round(v, 3)
+    return {"impl": "reference", "metric": "stage1_tok_per_s", "value": round(v, 3), "unit": "tokens/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(dt / a.steps * 1e3, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1] stage-1 (bounded sample: prefill T=48 + 16 decode steps per step)"},
+            "cpu_baseline": cb, "e2e": {"value": round(v, 3), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+if __name__ == "__main__":
+    main()

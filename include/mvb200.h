@@ -1,0 +1,142 @@
+/*
+ * mvb200.h -- C ABI of libmvb200.so: the B200 (sm_100a) engine behind MetaVoice-1B's
+ * TTS.synthesise() hot path.  Plain pointers and sizes only; no torch types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * reference tree metavoiceio/metavoice-src @ de3fa211).  Device buffers are owned by the
+ * caller (the Python shim allocates them as torch tensors and passes data_ptr()); the
+ * library never frees caller memory.  All functions return 0 on success, non-zero on
+ * failure with the message available from mvb_last_error().  A handle is re-entrant per
+ * handle, not thread-safe per handle (the reference is single-threaded per model,
+ * SURVEY.md 8b "Threading / state").
+ */
+#ifndef MVB200_H
+#define MVB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVB_ABI_VERSION 1
+
+/* KV-cache element type.  bf16 is what the reference stores (fast_model.py:97-102);
+ * fp32 is the validation mode used for the <=1e-3 parity gate against the fp32 oracle. */
+enum { MVB_KV_BF16 = 0, MVB_KV_FP32 = 1 };
+
+/* Shape of the stage-1 causal LM: fam/llm/fast_model.py:52-94 (ModelArgs / "metavoice-1B"). */
+typedef struct mvb_s1_config {
+  int32_t n_layer;       /* 24 */
+  int32_t n_head;        /* 16 (MHA: n_local_heads == n_head) */
+  int32_t head_dim;      /* 128 (only 128 is supported) */
+  int32_t dim;           /* 2048 */
+  int32_t intermediate;  /* 5632 */
+  int32_t vocab;         /* 2562 */
+  int32_t block_size;    /* 2048: learned-position table length and KV slots per row */
+  int32_t spk_dim;       /* 256 */
+  float   norm_eps;      /* 1e-5 */
+  int32_t max_utts;      /* utterance slots; each owns 2 CFG rows {cond, uncond} (fast_model.py:132-134) */
+  int32_t kv_dtype;      /* MVB_KV_BF16 | MVB_KV_FP32 */
+  int32_t max_new;       /* capacity of the per-utterance generated-token ring (<= block_size) */
+} mvb_s1_config;
+
+/* Byte offsets (into one bf16 weight arena) of every stage-1 tensor, row-major [out, in]
+ * exactly as stored in first_stage.pt.  Built by the checkpoint loader that
+ * replaces fast_inference_utils.py:236-281 (_load_model).  Per layer, in this order:
+ * attn_norm[dim], wqkv[3*dim, dim], wo[dim, dim], ffn_norm[dim], w1[inter, dim], w3[inter, dim],
+ * w2[dim, inter]. */
+#define MVB_S1_GLOBAL_TENSORS 5 /* tok_emb[vocab,dim], pos_emb[block,dim], spk_proj[dim,spk_dim], out_norm[dim], lm_head[vocab,dim] */
+#define MVB_S1_LAYER_TENSORS 7
+
+/* Sampling parameters of fast_inference_utils.py:107-120 (sample) for one utterance. */
+typedef struct mvb_sampling {
+  float    guidance_scale; /* g in g*cond + (1-g)*uncond */
+  float    temperature;    /* clamped below at 1e-5 (utils:92) */
+  float    top_p;          /* <= 0 disables (top_p=None) */
+  int32_t  top_k;          /* <= 0 disables (top_k=None) */
+  int32_t  end_of_audio;   /* token id that latches termination (2048; 9999 disables), utils:161 */
+  uint64_t seed;           /* Philox key for on-device Exp(1) noise when no noise buffer is supplied */
+} mvb_sampling;
+
+typedef struct mvb_s1 mvb_s1; /* opaque engine handle */
+
+int         mvb_abi_version(void);
+const char* mvb_last_error(void);
+
+/* Sizes the caller must allocate (device memory) before mvb_s1_create.
+ * Replaces Transformer.setup_caches (fast_model.py:136-148): KV = n_layer x {K,V} x rows x heads x
+ * block_size x head_dim elements. */
+size_t mvb_s1_kv_bytes(const mvb_s1_config* cfg);
+size_t mvb_s1_workspace_bytes(const mvb_s1_config* cfg);
+
+/* Build an engine over caller-owned device memory.  `offsets` is a HOST array of
+ * MVB_S1_GLOBAL_TENSORS + n_layer*MVB_S1_LAYER_TENSORS byte offsets into d_arena.  d_workspace must
+ * be zero-filled.  Replaces build_model()/Transformer.__init__/setup_caches/setup_spk_cond_mask
+ * (fast_inference_utils.py:324-352, fast_model.py:116-148); there is no JIT/compile step. */
+int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size_t arena_bytes,
+                  const uint64_t* offsets, void* d_kv, void* d_workspace, mvb_s1** out);
+int mvb_s1_destroy(mvb_s1* h);
+
+/* Hoisted speaker conditioning: spk_proj[utt] = W_spk * spk_emb (fast_model.py:152-157 recomputes it
+ * every step; it only changes per utterance).  d_spk_emb: fp32 [spk_dim] on device. */
+int mvb_s1_set_speaker(mvb_s1* h, int32_t utt, const float* d_spk_emb, void* stream);
+
+/* Parity hook == Transformer.forward(idx[2,S], spk_emb, input_pos=arange(pos0, pos0+S)) for slot
+ * `utt` (fast_model.py:150-163).  d_idx: int32 [2, S] on device (row 0 = cond, row 1 = uncond).
+ * Writes the KV cache at positions pos0..pos0+S-1.  d_logits: fp32 [2, S, vocab] when
+ * all_positions != 0, else fp32 [2, vocab] for the last position only. */
+int mvb_s1_forward(mvb_s1* h, int32_t utt, const int32_t* d_idx, int32_t S, int32_t pos0,
+                   float* d_logits, int32_t all_positions, void* stream);
+
+/* == sample() (fast_inference_utils.py:107-120) on device.  d_logits fp32 [2, vocab];
+ * d_noise: fp32 [vocab] Exp(1) draws (the reference's `q`, utils:64) or NULL for on-device Philox;
+ * d_token_out int32 [1]; d_probs_out fp32 [vocab] or NULL. */
+int mvb_s1_sample(mvb_s1* h, const float* d_logits, const mvb_sampling* p, const float* d_noise,
+                  uint64_t step, int32_t* d_token_out, float* d_probs_out, void* stream);
+
+/* Plugin call with HOST buffers == generate() (fast_inference_utils.py:181-228) for n_utts independent
+ * utterances decoded together (per-row positions; semantics of mixins/causal.py:179-287, which equal
+ * running each utterance alone).  Host->device copies of prompts/speaker vectors and the device->host
+ * copy of the tokens happen inside this call.
+ *   prompts      host int32, concatenated; prompt_lens[n_utts]
+ *   spk_embs     host fp32 [n_utts, spk_dim]
+ *   params       [n_utts]
+ *   noise        host or NULL: fp32 [n_utts, max_new_tokens, vocab] Exp(1) draws in the reference's call order
+ *   forced       host or NULL: int32 [n_utts, max_new_tokens] teacher-forced feedback tokens (test hook)
+ *   out_tokens   host int32 [n_utts, max_new_tokens]; out_lens[n_utts] = tokens produced (EOA included, utils:226)
+ * Raises (returns MVB_ERR_PROMPT_TOO_LONG) when a prompt leaves no room: utils:203-204. */
+int mvb_s1_generate(mvb_s1* h, int32_t n_utts, const int32_t* prompts, const int32_t* prompt_lens,
+                    const float* spk_embs, const mvb_sampling* params, int32_t max_new_tokens,
+                    const float* noise, const int32_t* forced, int32_t* out_tokens, int32_t* out_lens,
+                    void* stream);
+
+/* Same loop with inputs already resident: prompts/speakers must have been installed with
+ * mvb_s1_set_speaker + mvb_s1_forward (prefill).  Runs `n_steps` decode steps for utterances
+ * [0, n_utts) entirely on device (sampler, EOA latch and position bump included) and returns without
+ * a host sync.  Used by bench.py for the HBM-resident `value` and by the shim's generate(). */
+int mvb_s1_decode(mvb_s1* h, int32_t n_utts, int32_t n_steps, void* stream);
+
+/* Install per-utterance decode state after prefill: first token, sampling params, optional device
+ * noise [max_new, vocab] / forced-token [max_new] buffers (NULL = none). */
+int mvb_s1_begin(mvb_s1* h, int32_t utt, int32_t first_token, int32_t pos, const mvb_sampling* p,
+                 const float* d_noise, const int32_t* d_forced, void* stream);
+
+/* Read back decode state: tokens generated so far for `utt` (host buffer, capacity cap). */
+int mvb_s1_fetch(mvb_s1* h, int32_t utt, int32_t* out_tokens, int32_t cap, int32_t* n_out,
+                 int32_t* done, void* stream);
+
+/* Kernel launches issued by this handle since creation (bench.py "gpu_launches"). */
+uint64_t mvb_s1_launch_count(const mvb_s1* h);
+
+#define MVB_OK 0
+#define MVB_ERR_CUDA 1
+#define MVB_ERR_ARG 2
+#define MVB_ERR_PROMPT_TOO_LONG 3
+#define MVB_ERR_UNSUPPORTED 4
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVB200_H */

@@ -1,0 +1,484 @@
+// libmvb200: host side of the stage-1 engine and its C ABI (include/mvb200.h).
+// No torch, no CPU fallback: every entry point either runs the CUDA path or fails loudly.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mvb200.h"
+#include "stage1_kernels.cuh"
+
+using namespace mvb;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(MVB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+struct WsLayout {
+  size_t x, qkv, att, ffn, logits, spk, part_o, part_ml;
+  size_t slot_map, pos, row_tok, done, n_gen, gen_tokens, sampled, samp, noise, forced, ticket;
+  size_t stage_idx, stage_spk, stage_forced;
+  size_t total;
+};
+
+static WsLayout make_layout(const mvb_s1_config& c) {
+  WsLayout L;
+  const size_t U = c.max_utts, R = 2 * U, D = c.dim, F = c.intermediate, V = c.vocab, H = c.n_head;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes); return r; };
+  L.x = take(R * D * 4);
+  L.qkv = take(R * 3 * D * 4);
+  L.att = take(R * D * 4);
+  L.ffn = take(R * F * 4);
+  L.logits = take(R * V * 4);
+  L.spk = take(U * D * 4);
+  L.part_o = take(R * H * ATT_SPLITS * 128 * 4);
+  L.part_ml = take(R * H * ATT_SPLITS * 2 * 4);
+  L.slot_map = take(U * 4);
+  L.pos = take(U * 4);
+  L.row_tok = take(R * 4);
+  L.done = take(U * 4);
+  L.n_gen = take(U * 4);
+  L.gen_tokens = take(U * (size_t)c.max_new * 4);
+  L.sampled = take(U * (size_t)c.max_new * 4);
+  L.samp = take(U * sizeof(SamplingDev));
+  L.noise = take(U * sizeof(void*));
+  L.forced = take(U * sizeof(void*));
+  L.ticket = take(R * H * 4);
+  L.stage_idx = take(U * 2 * (size_t)c.block_size * 4);
+  L.stage_spk = take(U * (size_t)c.spk_dim * 4);
+  L.stage_forced = take(U * (size_t)c.max_new * 4);
+  L.total = o;
+  return L;
+}
+
+struct mvb_s1 {
+  mvb_s1_config cfg;
+  int n_sm = 148;
+  const char* arena = nullptr;
+  std::vector<uint64_t> off;
+  char* kv = nullptr;
+  char* ws = nullptr;
+  WsLayout L;
+  S1State st;
+  std::map<int, cudaGraphExec_t> graphs;
+  cudaStream_t cap_stream = nullptr;
+  uint64_t launches = 0;
+  int body_nodes = 0;
+  bool use_graph = true;
+  int* h_flags = nullptr;  // pinned: done flags / counters read back by generate()
+
+  template <typename T>
+  T* wsp(size_t o) const { return reinterpret_cast<T*>(ws + o); }
+  const __nv_bfloat16* w(int i) const { return reinterpret_cast<const __nv_bfloat16*>(arena + off[i]); }
+  const __nv_bfloat16* lw(int layer, int t) const { return w(MVB_S1_GLOBAL_TENSORS + layer * MVB_S1_LAYER_TENSORS + t); }
+  size_t kv_elem() const { return cfg.kv_dtype == MVB_KV_FP32 ? 4 : 2; }
+  size_t kv_half_bytes() const {
+    return (size_t)2 * cfg.max_utts * cfg.n_head * cfg.block_size * cfg.head_dim * kv_elem();
+  }
+};
+
+static int validate(const mvb_s1_config* c) {
+  if (!c) return fail(MVB_ERR_ARG, "null config");
+  if (c->head_dim != 128) return fail(MVB_ERR_UNSUPPORTED, "head_dim must be 128 (got %d)", c->head_dim);
+  if (c->dim != c->n_head * c->head_dim) return fail(MVB_ERR_ARG, "dim != n_head*head_dim");
+  if (c->dim % 256 || c->intermediate % 256) return fail(MVB_ERR_UNSUPPORTED, "dim and intermediate must be multiples of 256");
+  if (c->vocab % 2 || c->vocab > SAMP_PAD) return fail(MVB_ERR_UNSUPPORTED, "vocab must be even and <= %d", SAMP_PAD);
+  if (c->max_utts < 1 || c->max_utts > 64) return fail(MVB_ERR_ARG, "max_utts out of range");
+  if (c->max_new < 1 || c->max_new > c->block_size) return fail(MVB_ERR_ARG, "max_new out of range");
+  if (c->kv_dtype != MVB_KV_BF16 && c->kv_dtype != MVB_KV_FP32) return fail(MVB_ERR_ARG, "bad kv_dtype");
+  if ((size_t)c->intermediate * 8 > 48 * 1024 - 256) return fail(MVB_ERR_UNSUPPORTED, "intermediate too large for the staging buffer");
+  return MVB_OK;
+}
+
+extern "C" int mvb_abi_version(void) { return MVB_ABI_VERSION; }
+extern "C" const char* mvb_last_error(void) { return g_err.c_str(); }
+
+extern "C" size_t mvb_s1_kv_bytes(const mvb_s1_config* c) {
+  if (validate(c)) return 0;
+  const size_t esz = c->kv_dtype == MVB_KV_FP32 ? 4 : 2;
+  return (size_t)c->n_layer * 2 * (2 * (size_t)c->max_utts) * c->n_head * c->block_size * c->head_dim * esz;
+}
+
+extern "C" size_t mvb_s1_workspace_bytes(const mvb_s1_config* c) {
+  if (validate(c)) return 0;
+  return make_layout(*c).total;
+}
+
+extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size_t arena_bytes, const uint64_t* offsets,
+                             void* d_kv, void* d_ws, mvb_s1** out) {
+  if (int e = validate(cfg)) return e;
+  if (!d_arena || !offsets || !d_kv || !d_ws || !out) return fail(MVB_ERR_ARG, "null pointer argument");
+  int dev = 0, major = 0, minor = 0;
+  CK(cudaGetDevice(&dev));
+  CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10) return fail(MVB_ERR_UNSUPPORTED, "libmvb200 is built for sm_100a only; device is sm_%d%d", major, minor);
+  mvb_s1* h = new mvb_s1();
+  h->cfg = *cfg;
+  CK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dev));
+  h->arena = reinterpret_cast<const char*>(d_arena);
+  const int n_off = MVB_S1_GLOBAL_TENSORS + cfg->n_layer * MVB_S1_LAYER_TENSORS;
+  h->off.assign(offsets, offsets + n_off);
+  for (uint64_t o : h->off)
+    if (o % 16 || o >= arena_bytes) { delete h; return fail(MVB_ERR_ARG, "weight offset %llu not 16B-aligned or outside the arena", (unsigned long long)o); }
+  h->kv = reinterpret_cast<char*>(d_kv);
+  h->ws = reinterpret_cast<char*>(d_ws);
+  h->L = make_layout(*cfg);
+  S1State& s = h->st;
+  s.slot_map = h->wsp<int>(h->L.slot_map);
+  s.pos = h->wsp<int>(h->L.pos);
+  s.row_tok = h->wsp<int>(h->L.row_tok);
+  s.done = h->wsp<int>(h->L.done);
+  s.n_gen = h->wsp<int>(h->L.n_gen);
+  s.gen_tokens = h->wsp<int>(h->L.gen_tokens);
+  s.sampled_tokens = h->wsp<int>(h->L.sampled);
+  s.samp = h->wsp<SamplingDev>(h->L.samp);
+  s.noise = h->wsp<const float*>(h->L.noise);
+  s.forced = h->wsp<const int*>(h->L.forced);
+  s.attn_ticket = h->wsp<unsigned>(h->L.ticket);
+  s.max_new = cfg->max_new;
+  s.block_size = cfg->block_size;
+  h->use_graph = getenv("MVB_NO_GRAPH") == nullptr;
+  CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+  CK(cudaMallocHost(&h->h_flags, sizeof(int) * 4 * 64));
+  *out = h;
+  return MVB_OK;
+}
+
+extern "C" int mvb_s1_destroy(mvb_s1* h) {
+  if (!h) return MVB_OK;
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h->h_flags) cudaFreeHost(h->h_flags);
+  delete h;
+  return MVB_OK;
+}
+
+extern "C" uint64_t mvb_s1_launch_count(const mvb_s1* h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+static int gemv_grid(int n_items, int n_sm) {
+  const int cap = 2 * n_sm * 8;                       // resident warps at 2 CTAs/SM
+  const int ipw = (n_items + cap - 1) / cap;          // items per warp
+  return (n_items + 8 * ipw - 1) / (8 * ipw);
+}
+
+template <int EPI>
+static cudaError_t launch_gemv(mvb_s1* h, cudaStream_t s, int n_utts, GemvP p) {
+  const int n_items = (EPI == EPI_SWIGLU) ? p.M : p.M / 2;
+  dim3 grid(gemv_grid(n_items, h->n_sm), n_utts);
+  const size_t smem = (size_t)2 * p.K * sizeof(float);
+  k_gemv<EPI><<<grid, 256, smem, s>>>(p, h->st);
+  h->launches++;
+  return cudaGetLastError();
+}
+
+// One forward position for `n_utts` logical utterances: embed -> 24 x (attention, FFN) -> head.
+static int launch_body(mvb_s1* h, cudaStream_t s, int n_utts) {
+  const mvb_s1_config& c = h->cfg;
+  const int D = c.dim, F = c.intermediate, V = c.vocab, H = c.n_head;
+  float* x = h->wsp<float>(h->L.x);
+  float* qkv = h->wsp<float>(h->L.qkv);
+  float* att = h->wsp<float>(h->L.att);
+  float* ffn = h->wsp<float>(h->L.ffn);
+  float* logits = h->wsp<float>(h->L.logits);
+  k_embed<<<dim3(2, n_utts), 256, 0, s>>>(h->st, h->w(0), h->w(1), h->wsp<float>(h->L.spk), x, D);
+  h->launches++;
+  CK(cudaGetLastError());
+  const size_t half = h->kv_half_bytes();
+  for (int l = 0; l < c.n_layer; ++l) {
+    char* kc = h->kv + (size_t)l * 2 * half;
+    char* vc = kc + half;
+    GemvP p{};
+    p.eps = c.norm_eps;
+    // attention_norm + wqkv + cache scatter
+    p.W = h->lw(l, 1); p.W3 = nullptr; p.x = x; p.ldx = D; p.gain = h->lw(l, 0);
+    p.out = qkv; p.ldo = 3 * D; p.M = 3 * D; p.K = D;
+    p.kcache = kc; p.vcache = vc; p.H = H; p.S_max = c.block_size; p.D = D; p.kv_fp32 = c.kv_dtype == MVB_KV_FP32;
+    CK(launch_gemv<EPI_QKV>(h, s, n_utts, p));
+    // attention over [0, pos]
+    dim3 ag(H, 2 * n_utts, ATT_SPLITS);
+    if (c.kv_dtype == MVB_KV_FP32)
+      k_attn_decode<true><<<ag, 128, 0, s>>>(h->st, qkv, kc, vc, h->wsp<float>(h->L.part_o), h->wsp<float>(h->L.part_ml), att, H, c.block_size, D);
+    else
+      k_attn_decode<false><<<ag, 128, 0, s>>>(h->st, qkv, kc, vc, h->wsp<float>(h->L.part_o), h->wsp<float>(h->L.part_ml), att, H, c.block_size, D);
+    h->launches++;
+    CK(cudaGetLastError());
+    // wo + residual
+    p = GemvP{};
+    p.eps = c.norm_eps;
+    p.W = h->lw(l, 2); p.x = att; p.ldx = D; p.gain = nullptr; p.out = x; p.ldo = D; p.M = D; p.K = D;
+    CK(launch_gemv<EPI_RESID>(h, s, n_utts, p));
+    // ffn_norm + silu(w1 x) * w3 x
+    p.W = h->lw(l, 4); p.W3 = h->lw(l, 5); p.x = x; p.ldx = D; p.gain = h->lw(l, 3); p.out = ffn; p.ldo = F; p.M = F; p.K = D;
+    CK(launch_gemv<EPI_SWIGLU>(h, s, n_utts, p));
+    // w2 + residual
+    p.W = h->lw(l, 6); p.W3 = nullptr; p.x = ffn; p.ldx = F; p.gain = nullptr; p.out = x; p.ldo = D; p.M = D; p.K = F;
+    CK(launch_gemv<EPI_RESID>(h, s, n_utts, p));
+  }
+  GemvP p{};
+  p.eps = c.norm_eps;
+  p.W = h->w(4); p.x = x; p.ldx = D; p.gain = h->w(3); p.out = logits; p.ldo = V; p.M = V; p.K = D;
+  CK(launch_gemv<EPI_STORE>(h, s, n_utts, p));
+  return MVB_OK;
+}
+
+static int run_body(mvb_s1* h, cudaStream_t s, int n_utts) {
+  if (!h->use_graph) return launch_body(h, s, n_utts);
+  auto it = h->graphs.find(n_utts);
+  if (it == h->graphs.end()) {
+    cudaGraph_t g;
+    const uint64_t before = h->launches;
+    CK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    int e = launch_body(h, h->cap_stream, n_utts);
+    cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &g);
+    h->body_nodes = (int)(h->launches - before);
+    h->launches = before;
+    if (e) return e;
+    CK(ce);
+    cudaGraphExec_t ge;
+    CK(cudaGraphInstantiate(&ge, g, 0));
+    CK(cudaGraphDestroy(g));
+    it = h->graphs.emplace(n_utts, ge).first;
+  }
+  CK(cudaGraphLaunch(it->second, s));
+  h->launches += h->body_nodes;
+  return MVB_OK;
+}
+
+static SamplingDev to_dev(const mvb_sampling* p) {
+  SamplingDev d;
+  d.guidance = p->guidance_scale;
+  d.temperature = p->temperature;
+  d.top_p = p->top_p;
+  d.top_k = p->top_k;
+  d.end_of_audio = p->end_of_audio;
+  d.seed = p->seed;
+  return d;
+}
+
+extern "C" int mvb_s1_set_speaker(mvb_s1* h, int32_t utt, const float* d_spk, void* stream) {
+  if (!h || !d_spk) return fail(MVB_ERR_ARG, "null argument");
+  if (utt < 0 || utt >= h->cfg.max_utts) return fail(MVB_ERR_ARG, "utterance slot %d out of range", utt);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int D = h->cfg.dim;
+  k_spk_proj<<<(D * 32 + 255) / 256, 256, 0, s>>>(h->w(2), d_spk, h->wsp<float>(h->L.spk) + (size_t)utt * D, D, h->cfg.spk_dim);
+  h->launches++;
+  CK(cudaGetLastError());
+  return MVB_OK;
+}
+
+extern "C" int mvb_s1_forward(mvb_s1* h, int32_t utt, const int32_t* d_idx, int32_t S, int32_t pos0, float* d_logits,
+                              int32_t all_positions, void* stream) {
+  if (!h || !d_idx) return fail(MVB_ERR_ARG, "null argument");
+  if (utt < 0 || utt >= h->cfg.max_utts) return fail(MVB_ERR_ARG, "utterance slot %d out of range", utt);
+  if (S < 1 || pos0 < 0 || pos0 + S > h->cfg.block_size)
+    return fail(MVB_ERR_ARG, "positions [%d, %d) outside the %d-slot context", pos0, pos0 + S, h->cfg.block_size);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int V = h->cfg.vocab;
+  const float* lg = h->wsp<float>(h->L.logits) + (size_t)(2 * utt) * V;
+  for (int i = 0; i < S; ++i) {
+    k_set_input<<<1, 32, 0, s>>>(h->st, utt, d_idx, S, i, pos0 + i);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (int e = run_body(h, s, 1)) return e;
+    if (d_logits && all_positions) {
+      CK(cudaMemcpyAsync(d_logits + (size_t)i * V, lg, sizeof(float) * V, cudaMemcpyDeviceToDevice, s));
+      CK(cudaMemcpyAsync(d_logits + ((size_t)S + i) * V, lg + V, sizeof(float) * V, cudaMemcpyDeviceToDevice, s));
+    }
+  }
+  if (d_logits && !all_positions) CK(cudaMemcpyAsync(d_logits, lg, sizeof(float) * 2 * V, cudaMemcpyDeviceToDevice, s));
+  return MVB_OK;
+}
+
+extern "C" int mvb_s1_sample(mvb_s1* h, const float* d_logits, const mvb_sampling* p, const float* d_noise, uint64_t step,
+                             int32_t* d_token_out, float* d_probs_out, void* stream) {
+  if (!h || !d_logits || !p || !d_token_out) return fail(MVB_ERR_ARG, "null argument");
+  SampleP sp{};
+  sp.logits = d_logits;
+  sp.V = h->cfg.vocab;
+  sp.decode_mode = 0;
+  sp.sp = to_dev(p);
+  sp.noise = d_noise;
+  sp.step = step;
+  sp.token_out = d_token_out;
+  sp.probs_out = d_probs_out;
+  k_sample<<<1, SAMP_THREADS, 0, (cudaStream_t)stream>>>(sp, h->st);
+  h->launches++;
+  CK(cudaGetLastError());
+  return MVB_OK;
+}
+
+extern "C" int mvb_s1_begin(mvb_s1* h, int32_t utt, int32_t first_token, int32_t pos, const mvb_sampling* p,
+                            const float* d_noise, const int32_t* d_forced, void* stream) {
+  if (!h || !p) return fail(MVB_ERR_ARG, "null argument");
+  if (utt < 0 || utt >= h->cfg.max_utts) return fail(MVB_ERR_ARG, "utterance slot %d out of range", utt);
+  if (pos < 0 || pos >= h->cfg.block_size) return fail(MVB_ERR_ARG, "position %d outside the context", pos);
+  k_begin<<<1, 32, 0, (cudaStream_t)stream>>>(h->st, utt, first_token, pos, to_dev(p), d_noise, d_forced, first_token >= 0);
+  h->launches++;
+  CK(cudaGetLastError());
+  return MVB_OK;
+}
+
+static int sample_step(mvb_s1* h, cudaStream_t s, int n_utts) {
+  SampleP sp{};
+  sp.logits = h->wsp<float>(h->L.logits);
+  sp.V = h->cfg.vocab;
+  sp.decode_mode = 1;
+  k_sample<<<n_utts, SAMP_THREADS, 0, s>>>(sp, h->st);
+  h->launches++;
+  CK(cudaGetLastError());
+  return MVB_OK;
+}
+
+extern "C" int mvb_s1_decode(mvb_s1* h, int32_t n_utts, int32_t n_steps, void* stream) {
+  if (!h) return fail(MVB_ERR_ARG, "null handle");
+  if (n_utts < 1 || n_utts > h->cfg.max_utts) return fail(MVB_ERR_ARG, "n_utts %d out of range", n_utts);
+  cudaStream_t s = (cudaStream_t)stream;
+  k_identity_slots<<<1, 64, 0, s>>>(h->st, n_utts);
+  h->launches++;
+  CK(cudaGetLastError());
+  for (int i = 0; i < n_steps; ++i) {
+    if (int e = run_body(h, s, n_utts)) return e;
+    if (int e = sample_step(h, s, n_utts)) return e;
+  }
+  return MVB_OK;
+}
+
+extern "C" int mvb_s1_fetch(mvb_s1* h, int32_t utt, int32_t* out_tokens, int32_t cap, int32_t* n_out, int32_t* done,
+                            void* stream) {
+  if (!h) return fail(MVB_ERR_ARG, "null handle");
+  if (utt < 0 || utt >= h->cfg.max_utts) return fail(MVB_ERR_ARG, "utterance slot %d out of range", utt);
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(h->h_flags, h->st.n_gen + utt, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->h_flags + 1, h->st.done + utt, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const int n = h->h_flags[0];
+  if (n_out) *n_out = n;
+  if (done) *done = h->h_flags[1];
+  if (out_tokens && cap > 0) {
+    const int m = n < cap ? n : cap;
+    CK(cudaMemcpyAsync(out_tokens, h->st.gen_tokens + (size_t)utt * h->cfg.max_new, sizeof(int) * m, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
+  return MVB_OK;
+}
+
+// Sampled (pre-teacher-forcing) tokens, for the parity tests.
+extern "C" int mvb_s1_fetch_sampled(mvb_s1* h, int32_t utt, int32_t* out_tokens, int32_t cap, void* stream) {
+  if (!h || !out_tokens) return fail(MVB_ERR_ARG, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(out_tokens, h->st.sampled_tokens + (size_t)utt * h->cfg.max_new, sizeof(int) * cap, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return MVB_OK;
+}
+
+extern "C" int mvb_s1_generate(mvb_s1* h, int32_t n_utts, const int32_t* prompts, const int32_t* prompt_lens,
+                               const float* spk_embs, const mvb_sampling* params, int32_t max_new_tokens,
+                               const float* noise, const int32_t* forced, int32_t* out_tokens, int32_t* out_lens,
+                               void* stream) {
+  if (!h || !prompts || !prompt_lens || !spk_embs || !params || !out_tokens || !out_lens)
+    return fail(MVB_ERR_ARG, "null argument");
+  const mvb_s1_config& c = h->cfg;
+  if (n_utts < 1 || n_utts > c.max_utts) return fail(MVB_ERR_ARG, "n_utts %d exceeds the %d slots", n_utts, c.max_utts);
+  if (max_new_tokens < 1 || max_new_tokens > c.max_new) return fail(MVB_ERR_ARG, "max_new_tokens %d out of range", max_new_tokens);
+  cudaStream_t s = (cudaStream_t)stream;
+  // generate(): max_seq = min(T + max_new, block_size); raise if no room (utils:196-204)
+  std::vector<int> budget(n_utts);
+  for (int i = 0; i < n_utts; ++i) {
+    const int T = prompt_lens[i];
+    if (T < 1) return fail(MVB_ERR_ARG, "empty prompt for utterance %d", i);
+    const int room = (T + max_new_tokens < c.block_size ? T + max_new_tokens : c.block_size) - T;
+    if (room <= 0) return fail(MVB_ERR_PROMPT_TOO_LONG, "Prompt is too long to generate more tokens");
+    budget[i] = room;
+  }
+  const int V = c.vocab;
+  float* d_noise = nullptr;
+  if (noise) {
+    CK(cudaMalloc(&d_noise, sizeof(float) * (size_t)n_utts * max_new_tokens * V));
+    CK(cudaMemcpyAsync(d_noise, noise, sizeof(float) * (size_t)n_utts * max_new_tokens * V, cudaMemcpyHostToDevice, s));
+  }
+  int* d_forced = h->wsp<int>(h->L.stage_forced);
+  if (forced) CK(cudaMemcpyAsync(d_forced, forced, sizeof(int) * (size_t)n_utts * max_new_tokens, cudaMemcpyHostToDevice, s));
+  int* d_idx = h->wsp<int>(h->L.stage_idx);
+  float* d_spk = h->wsp<float>(h->L.stage_spk);
+  CK(cudaMemcpyAsync(d_spk, spk_embs, sizeof(float) * (size_t)n_utts * c.spk_dim, cudaMemcpyHostToDevice, s));
+  int rc = MVB_OK;
+  size_t poff = 0;
+  int max_budget = 0;
+  for (int i = 0; i < n_utts && rc == MVB_OK; ++i) {
+    const int T = prompt_lens[i];
+    int* di = d_idx + (size_t)i * 2 * c.block_size;
+    // prompt.view(1,-1).repeat(2,1): both CFG rows see the same tokens (utils:211)
+    CK(cudaMemcpyAsync(di, prompts + poff, sizeof(int) * T, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(di + T, prompts + poff, sizeof(int) * T, cudaMemcpyHostToDevice, s));
+    poff += T;
+    if ((rc = mvb_s1_set_speaker(h, i, d_spk + (size_t)i * c.spk_dim, s))) break;
+    mvb_sampling sp = params[i];
+    if ((rc = mvb_s1_begin(h, i, -1, 0, &sp, d_noise ? d_noise + (size_t)i * max_new_tokens * V : nullptr,
+                           forced ? d_forced + (size_t)i * max_new_tokens : nullptr, s))) break;
+    if ((rc = mvb_s1_forward(h, i, di, T, 0, nullptr, 0, s))) break;  // prefill (utils:123-132)
+    // first token sampled from the last prefill position (utils:211-212)
+    SampleP spp{};
+    spp.logits = h->wsp<float>(h->L.logits);
+    spp.V = V;
+    spp.decode_mode = 1;
+    k_sample<<<1, SAMP_THREADS, 0, s>>>(spp, h->st);  // slot_map[0] == i after the prefill
+    h->launches++;
+    if (cudaGetLastError() != cudaSuccess) { rc = fail(MVB_ERR_CUDA, "sampler launch failed"); break; }
+    if (budget[i] > max_budget) max_budget = budget[i];
+  }
+  // decode_n_tokens: at most budget-1 further steps, all utterances advance together with their own
+  // positions; per-utterance budgets are enforced by the done latch (n_gen >= budget -> host stops reading).
+  if (rc == MVB_OK) {
+    int remaining = max_budget - 1;
+    while (remaining > 0 && rc == MVB_OK) {
+      const int burst = remaining < 32 ? remaining : 32;
+      rc = mvb_s1_decode(h, n_utts, burst, s);
+      remaining -= burst;
+      if (rc) break;
+      CK(cudaMemcpyAsync(h->h_flags, h->st.done, sizeof(int) * n_utts, cudaMemcpyDeviceToHost, s));
+      CK(cudaStreamSynchronize(s));
+      bool all = true;
+      for (int i = 0; i < n_utts; ++i) all = all && h->h_flags[i];
+      if (all) break;
+    }
+  }
+  if (rc == MVB_OK) {
+    CK(cudaMemcpyAsync(h->h_flags, h->st.n_gen, sizeof(int) * n_utts, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (int i = 0; i < n_utts; ++i) {
+      int n = h->h_flags[i];
+      if (n > budget[i]) n = budget[i];
+      out_lens[i] = n;
+      CK(cudaMemcpyAsync(out_tokens + (size_t)i * max_new_tokens, h->st.gen_tokens + (size_t)i * c.max_new, sizeof(int) * n,
+                         cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+  }
+  if (d_noise) cudaFree(d_noise);
+  return rc;
+}

@@ -1,0 +1,180 @@
+"""Synthetic checkpoints in the reference's on-disk layout.
+
+No real MetaVoice weights exist offline, so every parity test and benchmark runs on
+seeded synthetic checkpoints that are laid out exactly like the files the reference
+loads:
+
+  * ``first_stage.pt``  -> dict(model=state_dict, model_args=..., config=..., meta=...)
+    read by ``fam/llm/fast_inference_utils.py:243-280`` (key names are the slow-path
+    ``GPT`` names: ``transformer.wtes.0.weight`` ... ``lm_heads.0.weight``).
+  * ``second_stage.pt`` -> same container, non-causal ``GPT`` with 2 input / 6 output
+    hierarchies, read by ``fam/llm/inference.py:102-141``.
+
+The generator is deterministic for a given (config, seed) on a given torch build, so the
+GPU box can regenerate bit-identical weights from the seed instead of shipping 2.5 GB.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, asdict
+from typing import Dict, Optional
+
+import torch
+
+
+@dataclass
+class Stage1Dims:
+    """Shape parameters of the stage-1 causal LM (fam/llm/fast_model.py:52-94)."""
+
+    n_layer: int = 24
+    n_head: int = 16
+    dim: int = 2048
+    vocab_size: int = 2562
+    block_size: int = 2048
+    speaker_emb_dim: int = 256
+    norm_eps: float = 1e-5
+    intermediate_size: Optional[int] = None
+
+    def __post_init__(self):
+        if self.intermediate_size is None:
+            # fam/llm/fast_model.py:69-72: find_multiple(int(2*4*dim/3), 256)
+            n_hidden = int(2 * 4 * self.dim / 3)
+            self.intermediate_size = n_hidden if n_hidden % 256 == 0 else n_hidden + 256 - (n_hidden % 256)
+
+    @property
+    def head_dim(self) -> int:
+        return self.dim // self.n_head
+
+    def n_params(self) -> int:
+        d, f, v = self.dim, self.intermediate_size, self.vocab_size
+        per_layer = 3 * d * d + d * d + 3 * d * f + 2 * d
+        return self.n_layer * per_layer + 2 * v * d + self.block_size * d + self.speaker_emb_dim * d + d
+
+
+FULL = Stage1Dims()
+TINY = Stage1Dims(n_layer=2, n_head=2, dim=256)
+
+
+def _normal(gen: torch.Generator, shape, std: float) -> torch.Tensor:
+    t = torch.empty(shape, dtype=torch.float32)
+    t.normal_(mean=0.0, std=std, generator=gen)
+    return t.to(torch.bfloat16)
+
+
+def stage1_state_dict(dims: Stage1Dims, seed: int = 0, tie_head: bool = False) -> Dict[str, torch.Tensor]:
+    """bf16 state dict with the reference checkpoint's key names.
+
+    Init follows GPT-2 style used by the reference (fam/llm/model.py:151-176): N(0, 0.02),
+    ``c_proj`` scaled by 1/sqrt(2*n_layer).  Norm gains are 1 + 0.1*N(0,1) rather than the
+    reference's all-ones so that the gain path is actually exercised by parity tests.
+    The LM head is drawn independently by default (the reference loads it as a separate
+    tensor, fast_inference_utils.py:252) so head and embedding mistakes cannot cancel.
+    """
+    gen = torch.Generator().manual_seed(seed)
+    d, f, v = dims.dim, dims.intermediate_size, dims.vocab_size
+    proj_std = 0.02 / math.sqrt(2 * dims.n_layer)
+    sd: Dict[str, torch.Tensor] = {}
+    sd["transformer.wtes.0.weight"] = _normal(gen, (v, d), 0.02)
+    sd["transformer.wpe.weight"] = _normal(gen, (dims.block_size, d), 0.02)
+    sd["speaker_cond_pos.weight"] = _normal(gen, (d, dims.speaker_emb_dim), 0.02)
+    for i in range(dims.n_layer):
+        p = f"transformer.h.{i}."
+        sd[p + "ln_1.weight"] = (1.0 + 0.1 * torch.empty(d).normal_(generator=gen)).to(torch.bfloat16)
+        sd[p + "attn.c_attn.weight"] = _normal(gen, (3 * d, d), 0.02)
+        sd[p + "attn.c_proj.weight"] = _normal(gen, (d, d), proj_std)
+        sd[p + "ln_2.weight"] = (1.0 + 0.1 * torch.empty(d).normal_(generator=gen)).to(torch.bfloat16)
+        sd[p + "mlp.swiglu.w1.weight"] = _normal(gen, (f, d), 0.02)
+        sd[p + "mlp.swiglu.w3.weight"] = _normal(gen, (f, d), 0.02)
+        sd[p + "mlp.c_proj.weight"] = _normal(gen, (d, f), proj_std)
+    sd["transformer.ln_f.weight"] = (1.0 + 0.1 * torch.empty(d).normal_(generator=gen)).to(torch.bfloat16)
+    if tie_head:
+        sd["lm_heads.0.weight"] = sd["transformer.wtes.0.weight"]
+    else:
+        sd["lm_heads.0.weight"] = _normal(gen, (v, d), 0.02)
+    return sd
+
+
+def state_dict_checksum(sd: Dict[str, torch.Tensor]) -> float:
+    """Cheap order-dependent fingerprint used by golden fixtures to detect RNG drift."""
+    acc = 0.0
+    for i, (k, t) in enumerate(sorted(sd.items())):
+        flat = t.reshape(-1)
+        step = max(1, flat.numel() // 4096)
+        acc += float(flat[::step].to(torch.float64).sum()) * (1.0 + 0.001 * (i % 97))
+    return acc
+
+
+def synthetic_tokenizer_meta(n_text_tokens: int = 512, offset: int = 2049) -> dict:
+    """``meta["tokenizer"]`` kwargs for ``TrainedBPETokeniser`` (fam/quantiser/text/tokenise.py:4-12).
+
+    256 single-byte tokens + (n_text_tokens-256) two-byte merges; EOT id = n_text_tokens so that
+    EOT + offset = 2561 as in the real checkpoint.
+    """
+    ranks = {bytes([b]): b for b in range(256)}
+    letters = b"etaoinshrdlucmfwypvbgkjqxz "
+    rank = 256
+    for a in letters:
+        for b in letters:
+            if rank >= n_text_tokens:
+                break
+            ranks[bytes([a, b])] = rank
+            rank += 1
+    assert rank == n_text_tokens
+    return dict(
+        name="synthetic_bpe",
+        pat_str=r"""'s|'t|'re|'ve|'m|'ll|'d| ?\w+| ?[^\s\w]+|\s+""",
+        mergeable_ranks=ranks,
+        special_tokens={"<|endoftext|>": n_text_tokens},
+        offset=offset,
+    )
+
+
+def stage1_checkpoint(dims: Stage1Dims, seed: int = 0) -> dict:
+    """Full ``first_stage.pt`` container."""
+    model_args = dict(
+        n_layer=dims.n_layer,
+        n_head=dims.n_head,
+        n_embd=dims.dim,
+        block_size=dims.block_size,
+        bias=False,
+        vocab_sizes=[dims.vocab_size],
+        causal=True,
+        target_vocab_sizes=None,
+        norm_type="rmsnorm",
+        rmsnorm_eps=dims.norm_eps,
+        nonlinearity_type="swiglu",
+        attn_kernel_type="torch_attn",
+        spk_emb_on_text=True,
+        swiglu_multiple_of=256,
+        dropout=0.0,
+    )
+    return dict(
+        model=stage1_state_dict(dims, seed),
+        model_args=model_args,
+        config=dict(causal=True),
+        meta=dict(tokenizer=synthetic_tokenizer_meta(), speaker_cond=True, speaker_emb_size=dims.speaker_emb_dim),
+        iter_num=0,
+        best_val_loss=0.0,
+    )
+
+
+def write_stage1_checkpoint(path, dims: Stage1Dims = FULL, seed: int = 0) -> None:
+    torch.save(stage1_checkpoint(dims, seed), str(path))
+
+
+def synthetic_prompt(T: int, seed: int = 7, text_lo: int = 2049, eot: int = 2561) -> torch.Tensor:
+    """T-1 text ids uniform in [2049, 2561) followed by EOT."""
+    gen = torch.Generator().manual_seed(seed)
+    ids = torch.randint(text_lo, eot, (T - 1,), generator=gen, dtype=torch.int64)
+    return torch.cat([ids, torch.tensor([eot])]).to(torch.int32)
+
+
+def synthetic_speaker(seed: int = 11, dim: int = 256) -> torch.Tensor:
+    """relu(N(0,1)) L2-normalised: same structure as speaker_encoder/model.py:57-58,101-102."""
+    gen = torch.Generator().manual_seed(seed)
+    e = torch.relu(torch.randn(1, dim, generator=gen))
+    return e / e.norm(dim=-1, keepdim=True)
+
+
+def dims_as_dict(d: Stage1Dims) -> dict:
+    return asdict(d)

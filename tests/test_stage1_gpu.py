@@ -1,0 +1,185 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against
+  (1) the committed golden vectors produced by the reference's own code, and
+  (2) the CPU oracle restatement on the same seeded inputs,
+plus size-independent properties (batched == single, cache-dtype bound, termination).
+Tolerance: north_star's 1e-3 relative (max-norm) on pre-sampling logits in validation mode (fp32 KV);
+token ids identical under identical noise."""
+import numpy as np
+import pytest
+import torch
+
+from mvb200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def _mk(dims, sd, kv="fp32", utts=1, max_new=None):
+    from mvb200.fast_model import ModelArgs, Transformer
+    cfg = ModelArgs(block_size=dims.block_size, vocab_size=dims.vocab_size, n_layer=dims.n_layer, n_head=dims.n_head,
+                    dim=dims.dim)
+    m = Transformer.from_state_dict(sd, cfg, device="cuda:0")
+    m.setup_caches(2 * utts, dims.block_size, kv_dtype=kv, max_new=max_new)
+    return m
+
+
+@pytest.fixture(scope="module")
+def tiny_sd():
+    return synth.stage1_state_dict(synth.TINY, 0)
+
+
+@pytest.fixture(scope="module")
+def full_sd():
+    return synth.stage1_state_dict(synth.FULL, 0)
+
+
+def _golden(golden_dir, name):
+    return np.load(f"{golden_dir}/{name}.npz")
+
+
+def _teacher_forced(model, g, last):
+    prompt = torch.from_numpy(g["prompt"]).cuda(); spk = torch.from_numpy(g["spk"]).cuda()
+    toks = torch.from_numpy(g["tokens"])
+    T = prompt.numel()
+    out = [model(prompt.view(1, -1).repeat(2, 1), spk, torch.arange(T))[:, -1].cpu()]
+    for s in range(1, last + 1):
+        t = toks[s - 1].view(1, 1).repeat(2, 1).cuda()
+        out.append(model(t, spk, torch.tensor([T + s - 1]))[:, -1].cpu())
+    return out
+
+
+def test_tiny_logits_vs_reference_golden(golden_dir, tiny_sd):
+    g = _golden(golden_dir, "stage1_tiny")
+    assert synth.state_dict_checksum(tiny_sd) == pytest.approx(float(g["weight_checksum"]), abs=1e-9)
+    m = _mk(synth.TINY, tiny_sd, "fp32")
+    steps = [int(s) for s in g["steps"]]
+    lg = _teacher_forced(m, g, max(steps))
+    errs = [_rel(lg[s], torch.from_numpy(g["logits"][i])) for i, s in enumerate(steps)]
+    print("tiny fp32-KV rel err per step", errs)
+    assert max(errs) < TOL
+
+
+def test_tiny_all_prefill_positions_vs_oracle(tiny_sd):
+    from oracle import stage1_port as P
+    d = synth.TINY
+    m = _mk(d, tiny_sd, "fp32")
+    o = P.Stage1Oracle(tiny_sd, d.n_head, d.norm_eps, torch.float32, faithful_full_cache=False); o.setup_caches()
+    prompt, spk = synth.synthetic_prompt(33, seed=3), synth.synthetic_speaker(seed=4)
+    idx = prompt.view(1, -1).repeat(2, 1)
+    idx[1, 5] = 2100  # rows may carry different tokens through the forward seam
+    got = m(idx.cuda(), spk.cuda(), torch.arange(33)).cpu()
+    want = o.forward(idx, spk, torch.arange(33))
+    assert got.shape == want.shape == (2, 33, d.vocab_size)
+    assert _rel(got, want) < TOL
+    # cond / uncond rows must differ (speaker conditioning active only on row 0)
+    assert (got[0] - got[1]).abs().max() > 1e-3
+
+
+def test_tiny_bf16_kv_bounded_by_reference_own_gap(golden_dir, tiny_sd):
+    g = _golden(golden_dir, "stage1_tiny")
+    m = _mk(synth.TINY, tiny_sd, "bf16")
+    steps = [int(s) for s in g["steps"]]
+    lg = _teacher_forced(m, g, max(steps))
+    for i, s in enumerate(steps):
+        ref32 = torch.from_numpy(g["logits"][i]); ref16 = torch.from_numpy(g["logits_ref_bf16"][i])
+        ours, theirs = _rel(lg[s], ref32), _rel(ref16, ref32)
+        print(f"step {s}: engine(bf16 KV) vs fp32 ref {ours:.2e}; reference bf16 vs fp32 ref {theirs:.2e}")
+        assert ours <= theirs
+
+
+def test_sampler_known_answers(golden_dir, tiny_sd):
+    from mvb200 import fast_inference_utils as U
+    g = _golden(golden_dir, "sampler")
+    m = _mk(synth.TINY, tiny_sd, "bf16")
+    for c in range(g["idx"].shape[0]):
+        gs, temp, tp, tk = [float(v) for v in g["params"][c]]
+        logits = torch.from_numpy(g["logits"][c])[:, None, :].cuda()
+        tok, probs = U.sample(logits, gs, temp, None if tp < 0 else tp, None if tk == 0 else int(tk), model=m,
+                              q=torch.from_numpy(g["noise"][c]))
+        assert int(tok) == int(g["idx"][c]), f"case {c}"
+        ref = torch.from_numpy(g["probs"][c])
+        assert torch.equal(probs.cpu() > 0, ref > 0), f"kept set differs in case {c}"
+        np.testing.assert_allclose(probs.cpu().numpy(), ref.numpy(), rtol=2e-5, atol=1e-9)
+
+
+def test_generate_reproduces_reference_tokens_with_reference_noise(golden_dir, tiny_sd):
+    """Feed the engine the Exp(1) draws the reference consumed (recomputed here with the same seed and call
+    order): token ids must be identical to the reference's (tests/golden/stage1_tiny.npz)."""
+    from mvb200 import fast_inference_utils as U
+    g = _golden(golden_dir, "stage1_tiny")
+    n = len(g["tokens"]); V = synth.TINY.vocab_size
+    torch.manual_seed(1337)
+    noise = torch.stack([torch.empty(V).exponential_(1) for _ in range(n)])
+    for i, s in enumerate(g["steps"]):
+        assert torch.equal(noise[int(s)], torch.from_numpy(g["noise"][i]))  # same generator stream as the reference
+    m = _mk(synth.TINY, tiny_sd, "fp32")
+    y = U.generate(m, torch.from_numpy(g["prompt"]), torch.from_numpy(g["spk"]), max_new_tokens=n,
+                   end_of_audio_token=9999, noise=noise, guidance_scale=float(g["guidance"]),
+                   temperature=float(g["temperature"]), top_p=float(g["top_p"]))
+    assert y[len(g["prompt"]):].tolist() == g["tokens"].tolist()
+
+
+def test_batched_mixed_lengths_equal_single_runs(tiny_sd):
+    """N utterances x 2 CFG rows with per-utterance positions == each utterance alone."""
+    from mvb200 import fast_inference_utils as U
+    d = synth.TINY
+    lens = [5, 17, 9]
+    prompts = [synth.synthetic_prompt(T, seed=20 + i) for i, T in enumerate(lens)]
+    spk = torch.cat([synth.synthetic_speaker(seed=30 + i) for i in range(3)])
+    n_new = 12
+    noise = torch.empty(3, n_new, d.vocab_size).exponential_(1, generator=torch.Generator().manual_seed(5))
+    mb = _mk(d, tiny_sd, "bf16", utts=3)
+    yb = U.generate_batch(mb, prompts, spk, max_new_tokens=n_new, end_of_audio_token=9999, noise=noise,
+                          guidance_scale=2.0, temperature=1.0, top_p=0.9)
+    ms = _mk(d, tiny_sd, "bf16", utts=1)
+    for i in range(3):
+        ys = U.generate_batch(ms, [prompts[i]], spk[i:i + 1], max_new_tokens=n_new, end_of_audio_token=9999,
+                              noise=noise[i:i + 1], guidance_scale=2.0, temperature=1.0, top_p=0.9)[0]
+        assert ys.tolist() == yb[i].tolist() and len(ys) == n_new
+
+
+def test_end_of_audio_latch_and_errors(tiny_sd):
+    from mvb200 import fast_inference_utils as U
+    d = synth.TINY
+    m = _mk(d, tiny_sd, "bf16", utts=2)
+    prompts = [synth.synthetic_prompt(6, seed=1), synth.synthetic_prompt(8, seed=2)]
+    spk = torch.cat([synth.synthetic_speaker(seed=1), synth.synthetic_speaker(seed=2)])
+    # teacher-force utterance 0 to emit EOA (2048) as its 3rd token: it must stop there, EOA included (utils:226)
+    forced = torch.full((2, 10), 100, dtype=torch.int32); forced[0, 2] = 2048
+    y = U.generate_batch(m, prompts, spk, max_new_tokens=10, end_of_audio_token=2048, forced=forced,
+                         guidance_scale=3.0, temperature=1.0, top_p=0.95)
+    assert y[0].tolist() == [100, 100, 2048] and len(y[1]) == 10
+    with pytest.raises(ValueError, match="Prompt is too long"):
+        U.generate_batch(m, [synth.synthetic_prompt(2048)], spk[:1], guidance_scale=3.0, temperature=1.0)
+    with pytest.raises(ValueError):
+        m(torch.zeros(2, 4, dtype=torch.int32).cuda(), spk[:1].cuda(), torch.tensor([0, 2, 3, 4]))
+    # last cache slot is usable: a single-token forward at position 2047
+    out = m(torch.full((2, 1), 7, dtype=torch.int32).cuda(), spk[:1].cuda(), torch.tensor([2047]))
+    assert torch.isfinite(out).all()
+
+
+def test_full_size_logits_vs_reference_golden(golden_dir, full_sd):
+    """The 1.2 B configuration BASELINE.json quotes, against logits the reference's own Transformer produced in
+    fp32 (prefill T=32 and teacher-forced decode steps 1, 8, 64)."""
+    g = _golden(golden_dir, "stage1_full")
+    assert synth.state_dict_checksum(full_sd) == pytest.approx(float(g["weight_checksum"]), abs=1e-9)
+    m = _mk(synth.FULL, full_sd, "fp32")
+    steps = [int(s) for s in g["steps"]]
+    lg = _teacher_forced(m, g, max(steps))
+    errs = [_rel(lg[s], torch.from_numpy(g["logits"][i])) for i, s in enumerate(steps)]
+    print("full fp32-KV rel err per step", errs)
+    assert max(errs) < TOL
+    m.close(); del m
+    torch.cuda.empty_cache()
+    mb = _mk(synth.FULL, full_sd, "bf16")
+    lg = _teacher_forced(mb, g, max(steps))
+    for i, s in enumerate(steps):
+        ref32 = torch.from_numpy(g["logits"][i]); ref16 = torch.from_numpy(g["logits_ref_bf16"][i])
+        ours, theirs = _rel(lg[s], ref32), _rel(ref16, ref32)
+        print(f"full step {s}: engine(bf16 KV) {ours:.2e} vs reference-bf16 {theirs:.2e}")
+        assert ours <= theirs
