@@ -130,6 +130,16 @@ int mvb_s1_fetch(mvb_s1* h, int32_t utt, int32_t* out_tokens, int32_t cap, int32
 /* Kernel launches issued by this handle since creation (bench.py "gpu_launches"). */
 uint64_t mvb_s1_launch_count(const mvb_s1* h);
 
+/* Tensor-core linear operator (tcgen05 + TMA weight streaming), the building block of the batched /
+ * prefill path and of the stage-2 model: y[R, M] (+)= f(x)[R, K] . W[M, K]^T, W bf16 row-major [out, in]
+ * as every nn.Linear weight in the reference checkpoints (e.g. fast_model.py:194-195, layers/attn.py:61-64).
+ * f = optional RMSNorm with bf16 gain (fast_model.py:250-261) when d_gain != NULL.  split_lo != 0 carries the
+ * activations as two bf16 terms (hi + lo) so the result matches an fp32-activation product to ~1e-5.
+ * K % 64 == 0, 1 <= R <= 128.  ksplit_override <= 0 selects the split automatically.  Synchronises `stream`. */
+int mvb_linear(const void* d_W, int32_t M, int32_t K, const float* d_x, int32_t ldx, int32_t R,
+               const void* d_gain, float eps, int32_t split_lo, int32_t ksplit_override, float* d_out,
+               int32_t ldo, int32_t accumulate, void* stream);
+
 #define MVB_OK 0
 #define MVB_ERR_CUDA 1
 #define MVB_ERR_ARG 2

@@ -12,6 +12,7 @@
 
 #include "../../include/mvb200.h"
 #include "stage1_kernels.cuh"
+#include "umma_host.cuh"
 
 using namespace mvb;
 
@@ -26,6 +27,17 @@ static int fail(int code, const char* fmt, ...) {
   g_err = buf;
   return code;
 }
+namespace mvb {
+int set_error(int code, const char* fmt, ...) {  // shared with the other translation units
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+}  // namespace mvb
 
 #define CK(expr)                                                                                   \
   do {                                                                                             \
@@ -40,8 +52,13 @@ struct WsLayout {
   size_t x, qkv, att, ffn, logits, spk, part_o, part_ml;
   size_t slot_map, pos, row_tok, done, n_gen, gen_tokens, sampled, samp, noise, forced, ticket;
   size_t stage_idx, stage_spk, stage_forced;
+  // path B (tensor-core rows path): activations for up to RB_MAX rows
+  size_t b_x, b_qkv, b_att, b_ffn, b_logits, b_last, b_B, b_rows, b_scratch, b_tickets, b_part_o, b_part_ml, b_att_tickets;
   size_t total;
 };
+
+constexpr int RB_MAX = 128;        // rows per tensor-core pass: 64-token prefill chunk x 2 CFG rows, or 64 utterances
+constexpr int PREFILL_CHUNK = 64;
 
 static WsLayout make_layout(const mvb_s1_config& c) {
   WsLayout L;
@@ -70,6 +87,28 @@ static WsLayout make_layout(const mvb_s1_config& c) {
   L.stage_idx = take(U * 2 * (size_t)c.block_size * 4);
   L.stage_spk = take(U * (size_t)c.spk_dim * 4);
   L.stage_forced = take(U * (size_t)c.max_new * 4);
+  {
+    const size_t RB = RB_MAX, NBM = 2 * RB_MAX;
+    L.b_x = take(RB * D * 4);
+    L.b_qkv = take(RB * 3 * D * 4);
+    L.b_att = take(RB * D * 4);
+    L.b_ffn = take(RB * F * 4);
+    L.b_logits = take(RB * V * 4);
+    L.b_last = take(2 * D * 4);
+    L.b_B = take(NBM * (F > D ? F : D) * 2);
+    L.b_rows = take(5 * RB * 4);
+    size_t sc = 0;
+    const size_t mats[5][3] = {{3 * D, D, 1}, {D, D, 1}, {F, D, 2}, {D, F, 1}, {V, D, 1}};
+    for (auto& m : mats) {
+      GemmPlan g = plan_gemm((int)m[0], (int)m[1], (int)NBM, m[2] == 2, 148);
+      if (g.scratch_floats > sc) sc = g.scratch_floats;
+    }
+    L.b_scratch = take(sc * 4);
+    L.b_tickets = take(256 * 4);
+    L.b_part_o = take(RB * H * ATT_SPLITS * 128 * 4);
+    L.b_part_ml = take(RB * H * ATT_SPLITS * 2 * 4);
+    L.b_att_tickets = take(RB * H * 4);
+  }
   L.total = o;
   return L;
 }
@@ -86,9 +125,15 @@ struct mvb_s1 {
   std::map<int, cudaGraphExec_t> graphs;
   cudaStream_t cap_stream = nullptr;
   uint64_t launches = 0;
-  int body_nodes = 0;
+  std::map<int, int> graph_nodes;
   bool use_graph = true;
   int* h_flags = nullptr;  // pinned: done flags / counters read back by generate()
+  // path B
+  std::vector<CUtensorMap> tmW;                       // per layer {wqkv, wo, w1, w3, w2}, then lm_head
+  std::map<std::pair<int, int>, CUtensorMap> tmB;     // (NB, K) -> activation buffer map
+  bool path_b = true;                                 // tensor-core rows path for batched decode and prefill
+  int split_lo = 1;                                   // carry activations as hi+lo bf16 terms
+  RowsDev rows;
 
   template <typename T>
   T* wsp(size_t o) const { return reinterpret_cast<T*>(ws + o); }
@@ -162,6 +207,25 @@ extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size
   s.max_new = cfg->max_new;
   s.block_size = cfg->block_size;
   h->use_graph = getenv("MVB_NO_GRAPH") == nullptr;
+  if (const char* e = getenv("MVB_PATHB")) h->path_b = atoi(e) != 0;
+  if (const char* e = getenv("MVB_SPLIT_LO")) h->split_lo = atoi(e) != 0;
+  {
+    int* rb = h->wsp<int>(h->L.b_rows);
+    h->rows.cache_row = rb; h->rows.pos = rb + RB_MAX; h->rows.tok = rb + 2 * RB_MAX; h->rows.utt = rb + 3 * RB_MAX;
+    h->rows.cond = rb + 4 * RB_MAX;
+    const int D = cfg->dim, F = cfg->intermediate;
+    h->tmW.resize((size_t)cfg->n_layer * 5 + 1);
+    bool ok = true;
+    for (int l = 0; l < cfg->n_layer && ok; ++l) {
+      ok = ok && make_tmap_bf16(&h->tmW[l * 5 + 0], h->lw(l, 1), 3 * D, D, 128);
+      ok = ok && make_tmap_bf16(&h->tmW[l * 5 + 1], h->lw(l, 2), D, D, 128);
+      ok = ok && make_tmap_bf16(&h->tmW[l * 5 + 2], h->lw(l, 4), F, D, 128);
+      ok = ok && make_tmap_bf16(&h->tmW[l * 5 + 3], h->lw(l, 5), F, D, 128);
+      ok = ok && make_tmap_bf16(&h->tmW[l * 5 + 4], h->lw(l, 6), D, F, 128);
+    }
+    ok = ok && make_tmap_bf16(&h->tmW[(size_t)cfg->n_layer * 5], h->w(4), cfg->vocab, D, 128);
+    if (!ok) { delete h; return fail(MVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight matrix"); }
+  }
   CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
   CK(cudaMallocHost(&h->h_flags, sizeof(int) * 4 * 64));
   *out = h;
@@ -246,26 +310,123 @@ static int launch_body(mvb_s1* h, cudaStream_t s, int n_utts) {
   return MVB_OK;
 }
 
-static int run_body(mvb_s1* h, cudaStream_t s, int n_utts) {
-  if (!h->use_graph) return launch_body(h, s, n_utts);
-  auto it = h->graphs.find(n_utts);
+
+// ------------------------------------------------------------------------------------------------
+// Path B: the same forward pass for R arbitrary activation rows on the tensor cores (umma_gemm.cuh).
+// Used for batched decode (R = 2 * n_utts) and for prefill chunks (R = 2 * tokens).
+static const CUtensorMap* tmap_b(mvb_s1* h, int NB, int K) {
+  auto key = std::make_pair(NB, K);
+  auto it = h->tmB.find(key);
+  if (it == h->tmB.end()) {
+    CUtensorMap tm;
+    if (!make_tmap_bf16(&tm, h->wsp<char>(h->L.b_B), (uint64_t)NB, (uint64_t)K, (uint32_t)NB)) return nullptr;
+    it = h->tmB.emplace(key, tm).first;
+  }
+  return &it->second;
+}
+
+struct LinB {
+  const float* x; int ldx; const __nv_bfloat16* gain;  // input rows (+ optional RMSNorm gain)
+  int widx, widx3;                                     // tensor-map indices of W (and W3 for SwiGLU)
+  int M, K;
+  float* out; int ldo;
+};
+
+template <int EPI>
+static int linear_b(mvb_s1* h, cudaStream_t s, int R, const LinB& a, void* kc = nullptr, void* vc = nullptr) {
+  const mvb_s1_config& c = h->cfg;
+  const int Rpad = (R + 15) / 16 * 16;
+  const int NB = Rpad * (h->split_lo ? 2 : 1);
+  const CUtensorMap* tB = tmap_b(h, NB, a.K);
+  if (!tB) return fail(MVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for the activation buffer");
+  __nv_bfloat16* B = h->wsp<__nv_bfloat16>(h->L.b_B);
+  k_prep_b<<<Rpad, 256, 0, s>>>(a.x, a.ldx, a.gain, c.norm_eps, a.K, Rpad, R, h->split_lo, B);
+  h->launches++;
+  CK(cudaGetLastError());
+  GemmP p{};
+  p.M = a.M; p.K = a.K; p.NB = NB; p.Rpad = Rpad; p.R = R; p.split_lo = h->split_lo;
+  p.scratch = h->wsp<float>(h->L.b_scratch);
+  p.tickets = h->wsp<unsigned>(h->L.b_tickets);
+  p.out = a.out; p.ldo = a.ldo;
+  p.kcache = kc; p.vcache = vc; p.row_cache = h->rows.cache_row; p.row_pos = h->rows.pos;
+  p.H = c.n_head; p.S_max = c.block_size; p.D = c.dim; p.kv_fp32 = c.kv_dtype == MVB_KV_FP32;
+  const GemmPlan g = plan_gemm(a.M, a.K, NB, EPI == G_SWIGLU, h->n_sm);
+  CK(launch_umma_gemm<EPI>(s, h->tmW[a.widx], h->tmW[a.widx3], *tB, p, g));
+  h->launches++;
+  return MVB_OK;
+}
+
+// embed + all layers for the R rows described by h->rows (already filled on the device)
+static int launch_layers_b(mvb_s1* h, cudaStream_t s, int R) {
+  const mvb_s1_config& c = h->cfg;
+  const int D = c.dim, F = c.intermediate, H = c.n_head;
+  float* x = h->wsp<float>(h->L.b_x);
+  float* qkv = h->wsp<float>(h->L.b_qkv);
+  float* att = h->wsp<float>(h->L.b_att);
+  float* ffn = h->wsp<float>(h->L.b_ffn);
+  k_embed_rows<<<R, 256, 0, s>>>(h->rows, h->w(0), h->w(1), h->wsp<float>(h->L.spk), x, D);
+  h->launches++;
+  CK(cudaGetLastError());
+  const size_t half = h->kv_half_bytes();
+  for (int l = 0; l < c.n_layer; ++l) {
+    char* kc = h->kv + (size_t)l * 2 * half;
+    char* vc = kc + half;
+    if (int e = linear_b<G_QKV>(h, s, R, LinB{x, D, h->lw(l, 0), l * 5 + 0, l * 5 + 0, 3 * D, D, qkv, 3 * D}, kc, vc)) return e;
+    dim3 ag(H, R, ATT_SPLITS);
+    if (c.kv_dtype == MVB_KV_FP32)
+      k_attn_rows<true><<<ag, 128, 0, s>>>(h->rows, qkv, kc, vc, h->wsp<float>(h->L.b_part_o), h->wsp<float>(h->L.b_part_ml),
+                                           h->wsp<unsigned>(h->L.b_att_tickets), att, H, c.block_size, D);
+    else
+      k_attn_rows<false><<<ag, 128, 0, s>>>(h->rows, qkv, kc, vc, h->wsp<float>(h->L.b_part_o), h->wsp<float>(h->L.b_part_ml),
+                                            h->wsp<unsigned>(h->L.b_att_tickets), att, H, c.block_size, D);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (int e = linear_b<G_RESID>(h, s, R, LinB{att, D, nullptr, l * 5 + 1, l * 5 + 1, D, D, x, D})) return e;
+    if (int e = linear_b<G_SWIGLU>(h, s, R, LinB{x, D, h->lw(l, 3), l * 5 + 2, l * 5 + 3, F, D, ffn, F})) return e;
+    if (int e = linear_b<G_RESID>(h, s, R, LinB{ffn, F, nullptr, l * 5 + 4, l * 5 + 4, D, F, x, D})) return e;
+  }
+  return MVB_OK;
+}
+
+// batched decode position: rows from the decode state, logits land in the sampler's buffer
+static int launch_body_b(mvb_s1* h, cudaStream_t s, int n_utts) {
+  const mvb_s1_config& c = h->cfg;
+  const int R = 2 * n_utts;
+  k_rows_decode<<<1, 128, 0, s>>>(h->st, h->rows, n_utts);
+  h->launches++;
+  CK(cudaGetLastError());
+  if (int e = launch_layers_b(h, s, R)) return e;
+  const int hw = c.n_layer * 5;
+  return linear_b<G_STORE>(h, s, R, LinB{h->wsp<float>(h->L.b_x), c.dim, h->w(3), hw, hw, c.vocab, c.dim,
+                                         h->wsp<float>(h->L.logits), c.vocab});
+}
+
+static int run_body(mvb_s1* h, cudaStream_t s, int n_utts, bool allow_b = true) {
+  // Path A (CUDA-core GEMV) streams the weights once per utterance; from 2 utterances up the tensor-core
+  // rows path streams them once per step for the whole batch.  slot_map must be the identity for path B
+  // (its logits rows are batch-ordered), which mvb_s1_decode guarantees.
+  const bool use_b = allow_b && h->path_b && n_utts >= 2;
+  auto body = [&](cudaStream_t st) { return use_b ? launch_body_b(h, st, n_utts) : launch_body(h, st, n_utts); };
+  if (!h->use_graph) return body(s);
+  const int key = n_utts + (use_b ? 1000 : 0);
+  auto it = h->graphs.find(key);
   if (it == h->graphs.end()) {
     cudaGraph_t g;
     const uint64_t before = h->launches;
     CK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
-    int e = launch_body(h, h->cap_stream, n_utts);
+    int e = body(h->cap_stream);
     cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &g);
-    h->body_nodes = (int)(h->launches - before);
+    h->graph_nodes[key] = (int)(h->launches - before);
     h->launches = before;
     if (e) return e;
     CK(ce);
     cudaGraphExec_t ge;
     CK(cudaGraphInstantiate(&ge, g, 0));
     CK(cudaGraphDestroy(g));
-    it = h->graphs.emplace(n_utts, ge).first;
+    it = h->graphs.emplace(key, ge).first;
   }
   CK(cudaGraphLaunch(it->second, s));
-  h->launches += h->body_nodes;
+  h->launches += h->graph_nodes[key];
   return MVB_OK;
 }
 
@@ -300,11 +461,47 @@ extern "C" int mvb_s1_forward(mvb_s1* h, int32_t utt, const int32_t* d_idx, int3
   cudaStream_t s = (cudaStream_t)stream;
   const int V = h->cfg.vocab;
   const float* lg = h->wsp<float>(h->L.logits) + (size_t)(2 * utt) * V;
+  if (h->path_b && S >= 2) {
+    // Prefill on the tensor cores in chunks of PREFILL_CHUNK tokens: every weight matrix is streamed once per
+    // chunk for all 2*Sc rows (the reference prefill, utils:123-132, does the same with a [2,T] batch).
+    const mvb_s1_config& c = h->cfg;
+    for (int s0 = 0; s0 < S; s0 += PREFILL_CHUNK) {
+      const int Sc = (S - s0) < PREFILL_CHUNK ? (S - s0) : PREFILL_CHUNK;
+      const int R = 2 * Sc;
+      k_rows_prefill<<<1, 128, 0, s>>>(h->rows, utt, d_idx, S, s0, Sc, pos0);
+      h->launches++;
+      CK(cudaGetLastError());
+      if (int e = launch_layers_b(h, s, R)) return e;
+      const int hw = c.n_layer * 5;
+      float* bx = h->wsp<float>(h->L.b_x);
+      if (d_logits && all_positions) {
+        float* bl = h->wsp<float>(h->L.b_logits);
+        if (int e = linear_b<G_STORE>(h, s, R, LinB{bx, c.dim, h->w(3), hw, hw, V, c.dim, bl, V})) return e;
+        for (int cc = 0; cc < 2; ++cc)
+          CK(cudaMemcpyAsync(d_logits + ((size_t)cc * S + s0) * V, bl + (size_t)cc * Sc * V, sizeof(float) * (size_t)Sc * V,
+                             cudaMemcpyDeviceToDevice, s));
+      }
+      if (s0 + Sc == S) {
+        // last position -> the sampler's logits rows of this utterance (and the decode state's position)
+        float* last = h->wsp<float>(h->L.b_last);
+        k_gather_last<<<2, 256, 0, s>>>(bx, last, Sc, c.dim);
+        h->launches++;
+        CK(cudaGetLastError());
+        if (int e = linear_b<G_STORE>(h, s, 2, LinB{last, c.dim, h->w(3), hw, hw, V, c.dim,
+                                                    h->wsp<float>(h->L.logits) + (size_t)(2 * utt) * V, V})) return e;
+        k_set_input<<<1, 32, 0, s>>>(h->st, utt, d_idx, S, S - 1, pos0 + S - 1);
+        h->launches++;
+        CK(cudaGetLastError());
+      }
+    }
+    if (d_logits && !all_positions) CK(cudaMemcpyAsync(d_logits, lg, sizeof(float) * 2 * V, cudaMemcpyDeviceToDevice, s));
+    return MVB_OK;
+  }
   for (int i = 0; i < S; ++i) {
     k_set_input<<<1, 32, 0, s>>>(h->st, utt, d_idx, S, i, pos0 + i);
     h->launches++;
     CK(cudaGetLastError());
-    if (int e = run_body(h, s, 1)) return e;
+    if (int e = run_body(h, s, 1, false)) return e;
     if (d_logits && all_positions) {
       CK(cudaMemcpyAsync(d_logits + (size_t)i * V, lg, sizeof(float) * V, cudaMemcpyDeviceToDevice, s));
       CK(cudaMemcpyAsync(d_logits + ((size_t)S + i) * V, lg + V, sizeof(float) * V, cudaMemcpyDeviceToDevice, s));

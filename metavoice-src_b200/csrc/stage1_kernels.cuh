@@ -274,19 +274,17 @@ __device__ __forceinline__ void load8(const void* base, size_t elem, float (&v)[
   }
 }
 
+// One (query row, head, KV split): q = query vector (fp32, 128), cache_row/L select the K/V slice,
+// pidx indexes the per-(row, head) partial slots, `ticket` is that pair's arrival counter.
 template <bool KV_FP32>
-__global__ void __launch_bounds__(128) k_attn_decode(S1State st, const float* __restrict__ qkv, const void* kcache,
-                                                     const void* vcache, float* __restrict__ part_o,
-                                                     float* __restrict__ part_ml, float* __restrict__ out, int H,
-                                                     int S_max, int D) {
+__device__ __forceinline__ void attn_core(const float* __restrict__ qvec, const void* kcache, const void* vcache,
+                                          int cache_row, int L, int h, int split, int H, int S_max,
+                                          float* __restrict__ part_o, float* __restrict__ part_ml, size_t pair,
+                                          unsigned* ticket, float* __restrict__ out_vec) {
   __shared__ float sm_o[8][128];
   __shared__ float sm_m[8], sm_l[8];
   __shared__ int sm_last;
-  const int h = blockIdx.x, split = blockIdx.z;
-  const int u = st.slot_map[blockIdx.y >> 1];
-  const int r = 2 * u + (blockIdx.y & 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, half = lane >> 4, sub = lane & 15;
-  const int L = st.pos[u] + 1;
   const int chunk = (((L + ATT_SPLITS - 1) / ATT_SPLITS) + 7) & ~7;
   const int start = split * chunk;
   const int end = min(L, start + chunk);
@@ -294,11 +292,10 @@ __global__ void __launch_bounds__(128) k_attn_decode(S1State st, const float* __
   float q[8];
   {
     const float scale = 0.08838834764831845f;  // 1/sqrt(128)
-    const float* qp = qkv + (size_t)r * 3 * D + h * 128 + sub * 8;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) q[i] = qp[i] * scale;
+    for (int i = 0; i < 8; ++i) q[i] = qvec[sub * 8 + i] * scale;
   }
-  const size_t row_base = ((size_t)r * H + h) * S_max * 128 + sub * 8;
+  const size_t row_base = ((size_t)cache_row * H + h) * S_max * 128 + sub * 8;
   float m = -INFINITY, l = 0.f, o[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = 0.f;
@@ -337,7 +334,7 @@ __global__ void __launch_bounds__(128) k_attn_decode(S1State st, const float* __
   for (int i = 0; i < 8; ++i) sm_o[g][sub * 8 + i] = o[i];
   __syncthreads();
 
-  const size_t pidx = ((size_t)r * H + h) * ATT_SPLITS + split;
+  const size_t pidx = pair * ATT_SPLITS + split;
   {
     float M = -INFINITY;
 #pragma unroll
@@ -360,13 +357,13 @@ __global__ void __launch_bounds__(128) k_attn_decode(S1State st, const float* __
   __threadfence();
   __syncthreads();
   if (tid == 0) {
-    const unsigned t = atomicAdd(&st.attn_ticket[r * H + h], 1u);
+    const unsigned t = atomicAdd(ticket, 1u);
     sm_last = (t == ATT_SPLITS - 1);
   }
   __syncthreads();
   if (sm_last) {
     __threadfence();
-    const size_t b = ((size_t)r * H + h) * ATT_SPLITS;
+    const size_t b = pair * ATT_SPLITS;
     float M = -INFINITY;
 #pragma unroll
     for (int i = 0; i < ATT_SPLITS; ++i) M = fmaxf(M, __ldcg(part_ml + (b + i) * 2));
@@ -380,9 +377,89 @@ __global__ void __launch_bounds__(128) k_attn_decode(S1State st, const float* __
         O += __ldcg(part_o + (b + i) * 128 + tid) * w;
       }
     }
-    out[(size_t)r * D + h * 128 + tid] = O / Ls;
-    if (tid == 0) st.attn_ticket[r * H + h] = 0u;
+    out_vec[tid] = O / Ls;
+    if (tid == 0) *ticket = 0u;
   }
+}
+
+// Path A: the two CFG rows of each utterance, positions from the decode state.
+template <bool KV_FP32>
+__global__ void __launch_bounds__(128) k_attn_decode(S1State st, const float* __restrict__ qkv, const void* kcache,
+                                                     const void* vcache, float* __restrict__ part_o,
+                                                     float* __restrict__ part_ml, float* __restrict__ out, int H,
+                                                     int S_max, int D) {
+  const int h = blockIdx.x, split = blockIdx.z;
+  const int u = st.slot_map[blockIdx.y >> 1];
+  const int r = 2 * u + (blockIdx.y & 1);
+  attn_core<KV_FP32>(qkv + (size_t)r * 3 * D + h * 128, kcache, vcache, r, st.pos[u] + 1, h, split, H, S_max, part_o,
+                     part_ml, (size_t)r * H + h, &st.attn_ticket[r * H + h], out + (size_t)r * D + h * 128);
+}
+
+// Path B: arbitrary activation rows (batched decode rows or the 2*S rows of a prefill chunk); each row
+// names its cache row and its own position, i.e. causal attention over [0, pos[row]].
+struct RowsDev {
+  int* cache_row;
+  int* pos;
+  int* tok;
+  int* utt;
+  int* cond;
+};
+
+template <bool KV_FP32>
+__global__ void __launch_bounds__(128) k_attn_rows(RowsDev rw, const float* __restrict__ qkv, const void* kcache,
+                                                   const void* vcache, float* __restrict__ part_o,
+                                                   float* __restrict__ part_ml, unsigned* tickets,
+                                                   float* __restrict__ out, int H, int S_max, int D) {
+  const int h = blockIdx.x, n = blockIdx.y, split = blockIdx.z;
+  attn_core<KV_FP32>(qkv + (size_t)n * 3 * D + h * 128, kcache, vcache, rw.cache_row[n], rw.pos[n] + 1, h, split, H, S_max,
+                     part_o, part_ml, (size_t)n * H + h, &tickets[n * H + h], out + (size_t)n * D + h * 128);
+}
+
+__global__ void k_rows_decode(S1State st, RowsDev rw, int n_utts) {
+  const int r = threadIdx.x;
+  if (r < 2 * n_utts) {
+    const int u = st.slot_map[r >> 1], c = r & 1;
+    rw.cache_row[r] = 2 * u + c;
+    rw.pos[r] = st.pos[u];
+    rw.tok[r] = st.row_tok[2 * u + c];
+    rw.utt[r] = u;
+    rw.cond[r] = (c == 0);
+  }
+}
+
+// rows of one prefill chunk: n = c * Sc + s  <->  (CFG row c, token s0 + s of idx[2, S])
+__global__ void k_rows_prefill(RowsDev rw, int utt, const int* __restrict__ idx, int S, int s0, int Sc, int pos0) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < 2 * Sc) {
+    const int c = n / Sc, s = n - c * Sc;
+    rw.cache_row[n] = 2 * utt + c;
+    rw.pos[n] = pos0 + s0 + s;
+    rw.tok[n] = idx[c * S + s0 + s];
+    rw.utt[n] = utt;
+    rw.cond[n] = (c == 0);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_embed_rows(RowsDev rw, const __nv_bfloat16* __restrict__ tok_emb,
+                                                    const __nv_bfloat16* __restrict__ pos_emb,
+                                                    const float* __restrict__ spk_proj, float* __restrict__ x, int D) {
+  const int n = blockIdx.x;
+  const __nv_bfloat16* te = tok_emb + (size_t)rw.tok[n] * D;
+  const __nv_bfloat16* pe = pos_emb + (size_t)rw.pos[n] * D;
+  const bool cond = rw.cond[n] != 0;
+  const float* sp = spk_proj + (size_t)rw.utt[n] * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float v = bf16_to_f32(te[d]) + bf16_to_f32(pe[d]);
+    if (cond) v += sp[d];
+    x[(size_t)n * D + d] = v;
+  }
+}
+
+// gather the two last-position rows of a prefill chunk (n = Sc-1 and 2*Sc-1) into rows {0, 1}
+__global__ void k_gather_last(const float* __restrict__ x, float* __restrict__ dst, int Sc, int D) {
+  const int c = blockIdx.x;
+  const float* src = x + (size_t)(c * Sc + Sc - 1) * D;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) dst[(size_t)c * D + d] = src[d];
 }
 
 // ---------------------------------------------------------------------------------------------

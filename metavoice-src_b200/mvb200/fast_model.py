@@ -131,10 +131,12 @@ class Transformer:
         self.spk_cond_mask = torch.zeros((2, 1, self.config.dim), dtype=torch.bool)
         self.spk_cond_mask[0] = 1
 
-    def setup_caches(self, max_batch_size: int, max_seq_length: int, kv_dtype: str = "bf16", max_new: Optional[int] = None):
-        """fast_model.py:136-148.  ``max_batch_size`` counts rows: 2 per utterance (CFG pair)."""
+    def setup_caches(self, max_batch_size: int, max_seq_length: int, kv_dtype: str = "bf16", max_new: Optional[int] = None,
+                     tensor_core_path: Optional[bool] = None):
+        """fast_model.py:136-148.  ``max_batch_size`` counts rows: 2 per utterance (CFG pair).
+        ``tensor_core_path`` (test hook): force the tcgen05 rows path on/off for prefill and batched decode."""
         if (self._handle is not None and self.max_seq_length >= max_seq_length and self.max_batch_size >= max_batch_size
-                and kv_dtype == self.kv_dtype):
+                and kv_dtype == self.kv_dtype and tensor_core_path is None):
             return
         c = self.config
         if max_batch_size % 2:
@@ -158,8 +160,21 @@ class Transformer:
         offs = (C.c_uint64 * len(self._offsets))(*self._offsets)
         h = C.c_void_p()
         torch.cuda.synchronize(self.device)
-        _lib.check(self._lib.mvb_s1_create(C.byref(cfg), self._arena.data_ptr(), self._arena.numel(), offs,
-                                           self._kv.data_ptr(), self._ws.data_ptr(), C.byref(h)))
+        import os
+        prev = os.environ.get("MVB_PATHB")
+        if tensor_core_path is not None:
+            os.environ["MVB_PATHB"] = "1" if tensor_core_path else "0"
+        try:
+            with torch.cuda.device(self.device):
+                rc = self._lib.mvb_s1_create(C.byref(cfg), self._arena.data_ptr(), self._arena.numel(), offs,
+                                             self._kv.data_ptr(), self._ws.data_ptr(), C.byref(h))
+        finally:
+            if tensor_core_path is not None:
+                if prev is None:
+                    os.environ.pop("MVB_PATHB", None)
+                else:
+                    os.environ["MVB_PATHB"] = prev
+        _lib.check(rc)
         self._handle = h
         self._spk_key = None
 

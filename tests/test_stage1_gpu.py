@@ -19,12 +19,12 @@ def _rel(a, b):
     return float((a - b).abs().max() / b.abs().max())
 
 
-def _mk(dims, sd, kv="fp32", utts=1, max_new=None):
+def _mk(dims, sd, kv="fp32", utts=1, max_new=None, tc=None):
     from mvb200.fast_model import ModelArgs, Transformer
     cfg = ModelArgs(block_size=dims.block_size, vocab_size=dims.vocab_size, n_layer=dims.n_layer, n_head=dims.n_head,
                     dim=dims.dim)
     m = Transformer.from_state_dict(sd, cfg, device="cuda:0")
-    m.setup_caches(2 * utts, dims.block_size, kv_dtype=kv, max_new=max_new)
+    m.setup_caches(2 * utts, dims.block_size, kv_dtype=kv, max_new=max_new, tensor_core_path=tc)
     return m
 
 
@@ -183,3 +183,41 @@ def test_full_size_logits_vs_reference_golden(golden_dir, full_sd):
         ours, theirs = _rel(lg[s], ref32), _rel(ref16, ref32)
         print(f"full step {s}: engine(bf16 KV) {ours:.2e} vs reference-bf16 {theirs:.2e}")
         assert ours <= theirs
+
+
+@pytest.mark.parametrize("tc", [False, True])
+def test_prefill_paths_vs_oracle_chunked(tiny_sd, tc):
+    """Prefill through the CUDA-core path (one position at a time) and through the tcgen05 rows path (64-token
+    chunks; T=70 crosses a chunk boundary), all positions, against the oracle; then a decode step on top of the
+    cache each path wrote."""
+    from oracle import stage1_port as P
+    d = synth.TINY
+    m = _mk(d, tiny_sd, "fp32", tc=tc)
+    o = P.Stage1Oracle(tiny_sd, d.n_head, d.norm_eps, torch.float32, faithful_full_cache=False); o.setup_caches()
+    T = 70
+    prompt, spk = synth.synthetic_prompt(T, seed=13), synth.synthetic_speaker(seed=14)
+    idx = prompt.view(1, -1).repeat(2, 1)
+    got = m(idx.cuda(), spk.cuda(), torch.arange(T)).cpu()
+    want = o.forward(idx, spk, torch.arange(T))
+    assert _rel(got, want) < TOL
+    t = torch.tensor([[1234], [1234]], dtype=torch.int32)
+    got = m(t.cuda(), spk.cuda(), torch.tensor([T])).cpu()
+    want = o.forward(t, spk, torch.tensor([T]))
+    assert _rel(got, want) < TOL
+
+
+def test_batched_decode_tensor_core_path_equals_cuda_core_path(tiny_sd):
+    from mvb200 import fast_inference_utils as U
+    d = synth.TINY
+    lens = [7, 21, 12, 30]
+    prompts = [synth.synthetic_prompt(T, seed=40 + i) for i, T in enumerate(lens)]
+    spk = torch.cat([synth.synthetic_speaker(seed=50 + i) for i in range(4)])
+    n_new = 16
+    noise = torch.empty(4, n_new, d.vocab_size).exponential_(1, generator=torch.Generator().manual_seed(6))
+    out = {}
+    for tc in (False, True):
+        m = _mk(d, tiny_sd, "fp32", utts=4, tc=tc)
+        out[tc] = U.generate_batch(m, prompts, spk, max_new_tokens=n_new, end_of_audio_token=9999, noise=noise,
+                                   guidance_scale=3.0, temperature=1.0, top_p=0.95)
+    for a, b in zip(out[False], out[True]):
+        assert a.tolist() == b.tolist() and len(a) == n_new
