@@ -132,6 +132,8 @@ struct mvb_s1 {
   std::vector<CUtensorMap> tmW;                       // per layer {wqkv, wo, w1, w3, w2}, then lm_head
   std::map<std::pair<int, int>, CUtensorMap> tmB;     // (NB, K) -> activation buffer map
   bool path_b = true;                                 // tensor-core rows path for batched decode and prefill
+  bool pdl = true;                                    // programmatic dependent launch between body kernels
+  int decode_b_min = 2;                               // utterances from which decode uses the tensor-core rows path
   int split_lo = 1;                                   // carry activations as hi+lo bf16 terms
   RowsDev rows;
 
@@ -208,6 +210,8 @@ extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size
   s.block_size = cfg->block_size;
   h->use_graph = getenv("MVB_NO_GRAPH") == nullptr;
   if (const char* e = getenv("MVB_PATHB")) h->path_b = atoi(e) != 0;
+  if (const char* e = getenv("MVB_PDL")) h->pdl = atoi(e) != 0;
+  if (const char* e = getenv("MVB_DECODE_B_MIN")) h->decode_b_min = atoi(e);
   if (const char* e = getenv("MVB_SPLIT_LO")) h->split_lo = atoi(e) != 0;
   {
     int* rb = h->wsp<int>(h->L.b_rows);
@@ -250,14 +254,31 @@ static int gemv_grid(int n_items, int n_sm) {
   return (n_items + 8 * ipw - 1) / (8 * ipw);
 }
 
+// Launch with the programmatic-dependent-launch attribute: the kernel may start while its predecessor in the
+// stream drains; it prefetches weights, then griddepcontrol.wait orders it after the predecessor's writes.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <int EPI>
 static cudaError_t launch_gemv(mvb_s1* h, cudaStream_t s, int n_utts, GemvP p) {
   const int n_items = (EPI == EPI_SWIGLU) ? p.M : p.M / 2;
   dim3 grid(gemv_grid(n_items, h->n_sm), n_utts);
   const size_t smem = (size_t)2 * p.K * sizeof(float);
-  k_gemv<EPI><<<grid, 256, smem, s>>>(p, h->st);
   h->launches++;
-  return cudaGetLastError();
+  return launch_pdl(h->pdl, k_gemv<EPI>, grid, dim3(256), smem, s, p, h->st);
 }
 
 // One forward position for `n_utts` logical utterances: embed -> 24 x (attention, FFN) -> head.
@@ -269,9 +290,9 @@ static int launch_body(mvb_s1* h, cudaStream_t s, int n_utts) {
   float* att = h->wsp<float>(h->L.att);
   float* ffn = h->wsp<float>(h->L.ffn);
   float* logits = h->wsp<float>(h->L.logits);
-  k_embed<<<dim3(2, n_utts), 256, 0, s>>>(h->st, h->w(0), h->w(1), h->wsp<float>(h->L.spk), x, D);
+  CK(launch_pdl(h->pdl, k_embed, dim3(2, n_utts), dim3(256), 0, s, h->st, h->w(0), h->w(1),
+                (const float*)h->wsp<float>(h->L.spk), x, D));
   h->launches++;
-  CK(cudaGetLastError());
   const size_t half = h->kv_half_bytes();
   for (int l = 0; l < c.n_layer; ++l) {
     char* kc = h->kv + (size_t)l * 2 * half;
@@ -286,11 +307,12 @@ static int launch_body(mvb_s1* h, cudaStream_t s, int n_utts) {
     // attention over [0, pos]
     dim3 ag(H, 2 * n_utts, ATT_SPLITS);
     if (c.kv_dtype == MVB_KV_FP32)
-      k_attn_decode<true><<<ag, 128, 0, s>>>(h->st, qkv, kc, vc, h->wsp<float>(h->L.part_o), h->wsp<float>(h->L.part_ml), att, H, c.block_size, D);
+      CK(launch_pdl(h->pdl, k_attn_decode<true>, ag, dim3(128), 0, s, h->st, (const float*)qkv, (const void*)kc, (const void*)vc,
+                    h->wsp<float>(h->L.part_o), h->wsp<float>(h->L.part_ml), att, H, c.block_size, D));
     else
-      k_attn_decode<false><<<ag, 128, 0, s>>>(h->st, qkv, kc, vc, h->wsp<float>(h->L.part_o), h->wsp<float>(h->L.part_ml), att, H, c.block_size, D);
+      CK(launch_pdl(h->pdl, k_attn_decode<false>, ag, dim3(128), 0, s, h->st, (const float*)qkv, (const void*)kc, (const void*)vc,
+                    h->wsp<float>(h->L.part_o), h->wsp<float>(h->L.part_ml), att, H, c.block_size, D));
     h->launches++;
-    CK(cudaGetLastError());
     // wo + residual
     p = GemvP{};
     p.eps = c.norm_eps;
@@ -405,7 +427,7 @@ static int run_body(mvb_s1* h, cudaStream_t s, int n_utts, bool allow_b = true) 
   // Path A (CUDA-core GEMV) streams the weights once per utterance; from 2 utterances up the tensor-core
   // rows path streams them once per step for the whole batch.  slot_map must be the identity for path B
   // (its logits rows are batch-ordered), which mvb_s1_decode guarantees.
-  const bool use_b = allow_b && h->path_b && n_utts >= 2;
+  const bool use_b = allow_b && h->path_b && n_utts >= h->decode_b_min;
   auto body = [&](cudaStream_t st) { return use_b ? launch_body_b(h, st, n_utts) : launch_body(h, st, n_utts); };
   if (!h->use_graph) return body(s);
   const int key = n_utts + (use_b ? 1000 : 0);

@@ -82,6 +82,8 @@ __global__ void k_identity_slots(S1State st, int n) {
 __global__ void __launch_bounds__(256) k_embed(S1State st, const __nv_bfloat16* __restrict__ tok_emb,
                                                const __nv_bfloat16* __restrict__ pos_emb,
                                                const float* __restrict__ spk_proj, float* __restrict__ x, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int u = st.slot_map[blockIdx.y];
   const int c = blockIdx.x;  // 0 = conditioned row, 1 = unconditioned row
   const int r = 2 * u + c;
@@ -129,14 +131,47 @@ __device__ __forceinline__ int xs_perm(int k) {
 }
 
 template <int EPI>
+__device__ __forceinline__ void gemv_rows(const GemvP& p, int item, int lane, const uint4*& wa, const uint4*& wb) {
+  if (EPI == EPI_SWIGLU) {
+    wa = reinterpret_cast<const uint4*>(p.W + (size_t)item * p.K) + lane;
+    wb = reinterpret_cast<const uint4*>(p.W3 + (size_t)item * p.K) + lane;
+  } else {
+    wa = reinterpret_cast<const uint4*>(p.W + (size_t)(2 * item) * p.K) + lane;
+    wb = wa + (p.K >> 3);
+  }
+}
+
+constexpr int GEMV_PF = 6;  // k-iterations (2 x 512 B per warp each) prefetched ahead of the dependency wait
+
+template <int EPI>
 __global__ void __launch_bounds__(256, 2) k_gemv(GemvP p, S1State st) {
   extern __shared__ float xs[];  // [2][K] permuted
   __shared__ float red[16];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = p.K;
+  const int n_items = (EPI == EPI_SWIGLU) ? p.M : (p.M >> 1);
+  const int nwarps = gridDim.x * 8;
+  const int KIT = K >> 8;
+  const int first = blockIdx.x * 8 + warp;
+
+  // ---- weights do not depend on the previous kernel: put the first GEMV_PF iterations of this warp's
+  //      first item in flight BEFORE waiting for the activations (programmatic dependent launch).
+  uint4 pa[GEMV_PF], pb[GEMV_PF];
+  if (first < n_items) {
+    const uint4 *wa, *wb;
+    gemv_rows<EPI>(p, first, lane, wa, wb);
+#pragma unroll
+    for (int i = 0; i < GEMV_PF; ++i)
+      if (i < KIT) {
+        pa[i] = ldg_stream(wa + i * 32);
+        pb[i] = ldg_stream(wb + i * 32);
+      }
+  }
+  pdl_launch_dependents();  // the next kernel may start ITS weight prefetch on free SM resources
+  pdl_wait();               // activations written by the previous kernel are now visible
+
   const int u = st.slot_map[blockIdx.y];
   const int r0 = 2 * u;
-  const int K = p.K;
-
   // ---- prologue: stage (and normalise) the two activation rows
   {
     const float* x0 = p.x + (size_t)r0 * p.ldx;
@@ -177,21 +212,28 @@ __global__ void __launch_bounds__(256, 2) k_gemv(GemvP p, S1State st) {
   }
 
   // ---- main: each warp streams two weight rows at a time
-  const int n_items = (EPI == EPI_SWIGLU) ? p.M : (p.M >> 1);
-  const int nwarps = gridDim.x * 8;
-  const int KIT = K >> 8;
-  for (int item = blockIdx.x * 8 + warp; item < n_items; item += nwarps) {
+  for (int item = first; item < n_items; item += nwarps) {
     const uint4 *wa, *wb;
-    if (EPI == EPI_SWIGLU) {
-      wa = reinterpret_cast<const uint4*>(p.W + (size_t)item * K) + lane;
-      wb = reinterpret_cast<const uint4*>(p.W3 + (size_t)item * K) + lane;
-    } else {
-      wa = reinterpret_cast<const uint4*>(p.W + (size_t)(2 * item) * K) + lane;
-      wb = wa + (K >> 3);
-    }
+    gemv_rows<EPI>(p, item, lane, wa, wb);
     float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;  // [weight row][activation row]
+    int it0 = 0;
+    if (item == first) {
+#pragma unroll
+      for (int i = 0; i < GEMV_PF; ++i)
+        if (i < KIT) {
+          const float4* xp = reinterpret_cast<const float4*>(xs + i * 256);
+          const float4* xq = reinterpret_cast<const float4*>(xs + K + i * 256);
+          const float4 x0a = xp[lane], x0b = xp[32 + lane];
+          const float4 x1a = xq[lane], x1b = xq[32 + lane];
+          fma8(a00, pa[i], x0a, x0b);
+          fma8(a01, pa[i], x1a, x1b);
+          fma8(a10, pb[i], x0a, x0b);
+          fma8(a11, pb[i], x1a, x1b);
+        }
+      it0 = KIT < GEMV_PF ? KIT : GEMV_PF;
+    }
 #pragma unroll 4
-    for (int it = 0; it < KIT; ++it) {
+    for (int it = it0; it < KIT; ++it) {
       const uint4 va = ldg_stream(wa + it * 32);
       const uint4 vb = ldg_stream(wb + it * 32);
       const float4* xp = reinterpret_cast<const float4*>(xs + it * 256);
@@ -388,6 +430,8 @@ __global__ void __launch_bounds__(128) k_attn_decode(S1State st, const float* __
                                                      const void* vcache, float* __restrict__ part_o,
                                                      float* __restrict__ part_ml, float* __restrict__ out, int H,
                                                      int S_max, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int h = blockIdx.x, split = blockIdx.z;
   const int u = st.slot_map[blockIdx.y >> 1];
   const int r = 2 * u + (blockIdx.y & 1);
