@@ -141,8 +141,6 @@ __device__ __forceinline__ void gemv_rows(const GemvP& p, int item, int lane, co
   }
 }
 
-constexpr int GEMV_PF = 6;  // k-iterations (2 x 512 B per warp each) prefetched ahead of the dependency wait
-
 template <int EPI>
 __global__ void __launch_bounds__(256, 2) k_gemv(GemvP p, S1State st) {
   extern __shared__ float xs[];  // [2][K] permuted
@@ -152,23 +150,8 @@ __global__ void __launch_bounds__(256, 2) k_gemv(GemvP p, S1State st) {
   const int n_items = (EPI == EPI_SWIGLU) ? p.M : (p.M >> 1);
   const int nwarps = gridDim.x * 8;
   const int KIT = K >> 8;
-  const int first = blockIdx.x * 8 + warp;
-
-  // ---- weights do not depend on the previous kernel: put the first GEMV_PF iterations of this warp's
-  //      first item in flight BEFORE waiting for the activations (programmatic dependent launch).
-  uint4 pa[GEMV_PF], pb[GEMV_PF];
-  if (first < n_items) {
-    const uint4 *wa, *wb;
-    gemv_rows<EPI>(p, first, lane, wa, wb);
-#pragma unroll
-    for (int i = 0; i < GEMV_PF; ++i)
-      if (i < KIT) {
-        pa[i] = ldg_stream(wa + i * 32);
-        pb[i] = ldg_stream(wb + i * 32);
-      }
-  }
-  pdl_launch_dependents();  // the next kernel may start ITS weight prefetch on free SM resources
-  pdl_wait();               // activations written by the previous kernel are now visible
+  pdl_launch_dependents();
+  pdl_wait();  // activations written by the previous kernel are now visible
 
   const int u = st.slot_map[blockIdx.y];
   const int r0 = 2 * u;
@@ -212,28 +195,12 @@ __global__ void __launch_bounds__(256, 2) k_gemv(GemvP p, S1State st) {
   }
 
   // ---- main: each warp streams two weight rows at a time
-  for (int item = first; item < n_items; item += nwarps) {
+  for (int item = blockIdx.x * 8 + warp; item < n_items; item += nwarps) {
     const uint4 *wa, *wb;
     gemv_rows<EPI>(p, item, lane, wa, wb);
     float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;  // [weight row][activation row]
-    int it0 = 0;
-    if (item == first) {
-#pragma unroll
-      for (int i = 0; i < GEMV_PF; ++i)
-        if (i < KIT) {
-          const float4* xp = reinterpret_cast<const float4*>(xs + i * 256);
-          const float4* xq = reinterpret_cast<const float4*>(xs + K + i * 256);
-          const float4 x0a = xp[lane], x0b = xp[32 + lane];
-          const float4 x1a = xq[lane], x1b = xq[32 + lane];
-          fma8(a00, pa[i], x0a, x0b);
-          fma8(a01, pa[i], x1a, x1b);
-          fma8(a10, pb[i], x0a, x0b);
-          fma8(a11, pb[i], x1a, x1b);
-        }
-      it0 = KIT < GEMV_PF ? KIT : GEMV_PF;
-    }
 #pragma unroll 4
-    for (int it = it0; it < KIT; ++it) {
+    for (int it = 0; it < KIT; ++it) {
       const uint4 va = ldg_stream(wa + it * 32);
       const uint4 vb = ldg_stream(wb + it * 32);
       const float4* xp = reinterpret_cast<const float4*>(xs + it * 256);

@@ -205,21 +205,37 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (*last_flag) {
         __threadfence();
-        const float* base = p.scratch + ((size_t)tile * p.ksplit * ncols) * 128;
-        for (int n = 0; n < p.R; ++n) {
-          float y = 0.f, y3 = 0.f;
-          for (int s = 0; s < p.ksplit; ++s) {  // fixed order -> run-to-run deterministic
-            const float* ps = base + ((size_t)s * ncols) * 128 + row_local;
-            float a = __ldcg(ps + (size_t)n * 128);
-            if (p.split_lo) a += __ldcg(ps + (size_t)(p.Rpad + n) * 128);
-            y += a;
-            if (NA == 2) {
-              float b = __ldcg(ps + (size_t)(p.NB + n) * 128);
-              if (p.split_lo) b += __ldcg(ps + (size_t)(p.NB + p.Rpad + n) * 128);
-              y3 += b;
+        const float* base = p.scratch + ((size_t)tile * p.ksplit * ncols) * 128 + row_local;
+        // 8 activation rows at a time: all loads of a group are independent and issued back to back
+        // (the serial version was latency-bound: R * ksplit dependent L2 round trips); the summation order over
+        // splits stays fixed -> run-to-run deterministic.
+        for (int n0 = 0; n0 < p.R; n0 += 8) {
+          float y[8], y3[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) y[i] = y3[i] = 0.f;
+          for (int s = 0; s < p.ksplit; ++s) {
+            const float* ps = base + ((size_t)s * ncols) * 128;
+            float a[8], al[8], b3[8], bl[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int n = n0 + i;
+              const bool ok = n < p.R;
+              a[i] = ok ? __ldcg(ps + (size_t)n * 128) : 0.f;
+              al[i] = (ok && p.split_lo) ? __ldcg(ps + (size_t)(p.Rpad + n) * 128) : 0.f;
+              if (NA == 2) {
+                b3[i] = ok ? __ldcg(ps + (size_t)(p.NB + n) * 128) : 0.f;
+                bl[i] = (ok && p.split_lo) ? __ldcg(ps + (size_t)(p.NB + p.Rpad + n) * 128) : 0.f;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              y[i] += a[i] + al[i];
+              if (NA == 2) y3[i] += b3[i] + bl[i];
             }
           }
-          if (j < p.M) gemm_apply<EPI>(p, n, j, y, y3);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (n0 + i < p.R && j < p.M) gemm_apply<EPI>(p, n0 + i, j, y[i], y3[i]);
         }
         if (tid == 128) p.tickets[tile] = 0u;
       }
