@@ -127,6 +127,12 @@ int mvb_s1_begin(mvb_s1* h, int32_t utt, int32_t first_token, int32_t pos, const
 int mvb_s1_fetch(mvb_s1* h, int32_t utt, int32_t* out_tokens, int32_t cap, int32_t* n_out,
                  int32_t* done, void* stream);
 
+/* Parity hook for the persistent fused decode kernel: one decode position (== Transformer.forward with S = 1,
+ * fast_model.py:150-163) for utterances [0, n_utts) from the state installed by mvb_s1_begin, through the single
+ * persistent kernel; logits fp32 [2*n_utts, vocab] are copied to d_logits, nothing is sampled, positions do not
+ * advance (the KV cache is appended at the current positions). */
+int mvb_s1_step_logits(mvb_s1* h, int32_t n_utts, float* d_logits, void* stream);
+
 /* Kernel launches issued by this handle since creation (bench.py "gpu_launches"). */
 uint64_t mvb_s1_launch_count(const mvb_s1* h);
 

@@ -1,0 +1,646 @@
+// Path C: ONE persistent kernel per decode position (fast_model.py:150-163 for S = 1), all 24 layers.
+//
+//   * grid = one CTA per SM; every CTA owns a static slice of every weight matrix:
+//       (K split s = cta % S, row tiles t = cta / S, + groups, ...)  chosen per matrix on the host.
+//   * warp 0 = PRODUCER: one thread walks the whole step's byte schedule -- weight tiles via TMA
+//     (cp.async.bulk.tensor, 128B swizzle) and KV-cache tiles via cp.async.bulk -- into a ring of 16 KB smem
+//     stages guarded by full/empty mbarriers.  Weights and old KV do not depend on this step's activations,
+//     so the producer never waits for a grid barrier: the HBM stream keeps running across phase boundaries.
+//   * warp 1 = MMA ISSUER: one thread issues tcgen05.mma (M=128 weight rows x N=32 activation columns,
+//     fp32 accumulators double-buffered in TMEM) straight from the ring; activations are the exact
+//     hi+lo bf16 split of the fp32 vectors, so products match fp32-activation math to ~1e-5.
+//   * warps 2..5 = COMPUTE: wait for the previous phase grid-wide (split arrive/wait counter), stage the
+//     B operand into swizzled smem (RMSNorm / attention-merge / SiLU*mul fused here), run the epilogues
+//     (tcgen05.ld -> red.global.add.f32 split-K accumulation) and the decode attention on smem KV tiles
+//     (online softmax per half-warp).
+//   * phases per layer: QKV | attention (+KV-cache append) | wo+residual | w1,w3 | w2+residual, then head.
+//     5 grid-wide dependencies per layer, no host involvement, no per-layer launch.
+#pragma once
+#include "stage1_kernels.cuh"
+#include "umma.cuh"
+
+namespace mvb {
+
+constexpr int PC_THREADS = 192;      // producer warp + MMA warp + 4 compute warps
+constexpr int PC_STAGES = 10;        // ring depth (x 16 KB)
+constexpr int PC_STAGE_BYTES = 16384;
+constexpr int PC_NB = 32;            // UMMA N: 16 hi rows + 16 lo rows
+constexpr int PC_RPAD = 16;          // max activation rows (8 utterances x 2 CFG rows)
+constexpr int PC_BKB_MAX = 12;       // k-blocks of B one CTA may own in a phase
+constexpr int PC_B_BYTES = PC_BKB_MAX * PC_NB * 128;
+constexpr int PC_ATT_CHUNK_BYTES = PC_STAGE_BYTES;  // one KV tile = one ring stage
+constexpr int PC_MAX_CHUNKS = 64;    // per (row, head): ceil(2048 / 32) in fp32 mode
+
+struct PcMat {     // one weight matrix kind, static decomposition
+  int T;           // row tiles (of 128)
+  int KB;          // k-blocks (of 64)
+  int S;           // K splits
+  int G;           // tile groups = gridDim / S
+};
+
+struct PcParams {
+  int n_layer, D, F, V, H, S_max, R, n_utts, kv_fp32;
+  float eps;
+  PcMat m_qkv, m_o, m_w13, m_w2, m_head;
+  const __nv_bfloat16* attn_norm;   // layer 0; layer l at + l * layer_stride
+  const __nv_bfloat16* ffn_norm;
+  const __nv_bfloat16* out_norm;
+  size_t layer_stride;              // elements between consecutive layers' tensors
+  const __nv_bfloat16* tok_emb;
+  const __nv_bfloat16* pos_emb;
+  const float* spk_proj;
+  float* x;        // [RPAD, D]   residual stream (red.add target of wo / w2)
+  float* qkv;      // [RPAD, 3D]  red.add target, zeroed during the wo phase
+  float* gu;       // [RPAD, 2F]  g | u, red.add target, zeroed during the attention phase
+  float* logits;   // [2*max_utts, V] sampler buffer (zeroed by the sampler after use)
+  float* part_o;   // [RPAD*H*PC_MAX_CHUNKS, 128]
+  float* part_ml;  // [RPAD*H*PC_MAX_CHUNKS, 2]
+  char* kv;
+  size_t kv_half;  // bytes of one layer's K (or V) region
+  unsigned* bar;   // grid-wide arrival counter (zero at launch)
+  S1State st;
+};
+
+// ---- small device helpers -------------------------------------------------------------------------
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
+}
+
+// byte offset of the 16-byte chunk holding k..k+7 of activation row `row` inside the B operand
+// (K-major, 128B swizzle, [k-block][NB rows][128 B])
+__device__ __forceinline__ uint32_t b_chunk_off(int kb_local, int row, int kchunk /* (k % 64) / 8 */) {
+  return (uint32_t)(kb_local * (PC_NB * 128) + (row >> 3) * 1024 + (row & 7) * 128 + ((kchunk ^ (row & 7)) << 4));
+}
+
+// split 8 fp32 into bf16 hi / lo and store both rows' chunks
+__device__ __forceinline__ void b_store8(uint8_t* B, int kb_local, int n, int kchunk, const float (&v)[8]) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
+    hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  *reinterpret_cast<uint4*>(B + b_chunk_off(kb_local, n, kchunk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(B + b_chunk_off(kb_local, PC_RPAD + n, kchunk)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+struct PcSlice {   // what this CTA owns of one matrix
+  int kb0, kb1, t0, nt, G;
+};
+__device__ __forceinline__ PcSlice pc_slice(const PcMat& m, int cta) {
+  PcSlice s;
+  const int sp = cta % m.S, g = cta / m.S;
+  s.kb0 = (int)(((long long)sp * m.KB) / m.S);
+  s.kb1 = (int)(((long long)(sp + 1) * m.KB) / m.S);
+  s.G = m.G;
+  s.t0 = g;
+  s.nt = (g < m.G && g < m.T) ? (m.T - g + m.G - 1) / m.G : 0;
+  return s;
+}
+
+// attention work list of this CTA: units (row, head, chunk) round-robin over CTAs
+struct PcAtt {
+  int pos_per_chunk;   // positions per 16 KB tile
+  int total;           // units in this layer
+};
+
+__device__ __forceinline__ int att_chunks(int L, int ppc) { return (L + ppc - 1) / ppc; }
+
+template <bool KV_FP32>
+__device__ __forceinline__ void load8s(const uint8_t* tile, int p, int sub, float (&v)[8]) {
+  if (KV_FP32) {
+    const float4* q = reinterpret_cast<const float4*>(tile + (size_t)p * 512 + sub * 32);
+    const float4 a = q[0], b = q[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 w = *reinterpret_cast<const uint4*>(tile + (size_t)p * 256 + sub * 16);
+    v[0] = bf_lo(w.x); v[1] = bf_hi(w.x); v[2] = bf_lo(w.y); v[3] = bf_hi(w.y);
+    v[4] = bf_lo(w.z); v[5] = bf_hi(w.z); v[6] = bf_lo(w.w); v[7] = bf_hi(w.w);
+  }
+}
+
+template <bool KV_FP32>
+__global__ void __launch_bounds__(PC_THREADS, 1)
+k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_o,
+                    const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w3,
+                    const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_head,
+                    const PcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* ring = smem;
+  uint8_t* Bop = smem + PC_STAGES * PC_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Bop + PC_B_BYTES);
+  // bars: full[S] empty[S] b_ready acc_full[2] acc_empty[2]
+  uint64_t* b_full = bars;
+  uint64_t* b_empty = bars + PC_STAGES;
+  uint64_t* b_ready = bars + 2 * PC_STAGES;
+  uint64_t* acc_full = b_ready + 1;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sm_f = reinterpret_cast<float*>(tmem_slot + 4);   // [8][128] o, [8] m, [8] l, [PC_RPAD] rstd  (compute scratch)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cta = blockIdx.x, G = gridDim.x;
+  const int esz = KV_FP32 ? 4 : 2;
+  const int ppc = PC_ATT_CHUNK_BYTES / (128 * esz);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < PC_STAGES; ++s) {
+      ptx::mbar_init(ptx::smem_u32(b_full + s), 1);
+      ptx::mbar_init(ptx::smem_u32(b_empty + s), 1);
+    }
+    ptx::mbar_init(ptx::smem_u32(b_ready), 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(ptx::smem_u32(acc_full + i), 1);
+      ptx::mbar_init(ptx::smem_u32(acc_empty + i), 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 64);
+    ptx::tmem_relinquish();
+  }
+  // zero the B operand once: rows >= R (and the unused hi/lo padding rows) must read as zero forever
+  for (int i = tid; i < PC_B_BYTES / 16; i += PC_THREADS) reinterpret_cast<uint4*>(Bop)[i] = make_uint4(0, 0, 0, 0);
+  fence_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+
+  const PcSlice s_qkv = pc_slice(p.m_qkv, cta), s_o = pc_slice(p.m_o, cta), s_w13 = pc_slice(p.m_w13, cta),
+                s_w2 = pc_slice(p.m_w2, cta), s_head = pc_slice(p.m_head, cta);
+  const int T1 = p.m_w13.T >> 1;  // w1 tiles; tiles >= T1 belong to w3
+
+  if (warp == 0) {
+    // =================================== PRODUCER ===================================================
+    if (lane == 0) {
+      const uint64_t pol = ptx::policy_evict_first();
+      uint32_t slot = 0;
+      auto acquire = [&]() -> uint32_t {   // returns stage index; waits until the consumer released it
+        const uint32_t s = slot % PC_STAGES, ph = (slot / PC_STAGES) & 1u;
+        ptx::mbar_wait(ptx::smem_u32(b_empty + s), ph ^ 1u);
+        ++slot;
+        return s;
+      };
+      auto gemm_tiles = [&](const CUtensorMap* tmA, const CUtensorMap* tmB2, int split_t, const PcSlice& sl, int layer) {
+        for (int i = 0; i < sl.nt; ++i) {
+          const int t = sl.t0 + i * sl.G;
+          const CUtensorMap* tm = (t < split_t) ? tmA : tmB2;
+          const int tt = (t < split_t) ? t : t - split_t;
+          for (int kb = sl.kb0; kb < sl.kb1; ++kb) {
+            const uint32_t s = acquire();
+            const uint32_t full = ptx::smem_u32(b_full + s);
+            ptx::mbar_arrive_expect_tx(full, PC_STAGE_BYTES);
+            tma_load_3d(ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES), tm, full, kb * 64, tt * 128, layer, pol);
+          }
+        }
+      };
+      bool waited = false;
+      for (int l = 0; l < p.n_layer; ++l) {
+        gemm_tiles(&tm_qkv, &tm_qkv, 1 << 30, s_qkv, l);
+        // ---- KV tiles of this CTA's attention units (positions < pos are from earlier steps)
+        if (!waited) { pdl_wait(); waited = true; }   // pos[] is written by the previous sampler kernel
+        {
+          const char* kbase = p.kv + (size_t)l * 2 * p.kv_half;
+          const char* vbase = kbase + p.kv_half;
+          int unit0 = 0;
+          for (int r = 0; r < p.R; ++r) {
+            const int u = p.st.slot_map[r >> 1];
+            const int cr = 2 * u + (r & 1);
+            const int L = p.st.pos[u] + 1;
+            const int nch = att_chunks(L, ppc);
+            for (int h = 0; h < p.H; ++h) {
+              // units of (r, h) are unit0 + [0, nch); this CTA takes those == cta (mod G)
+              int first = (cta - (unit0 % G) + G) % G;
+              for (int c = first; c < nch; c += G) {
+                const int p0 = c * ppc;
+                const int pend = min(L - 1, p0 + ppc);        // the current position comes from registers
+                const int npos = pend - p0;
+                if (npos > 0) {
+                  const size_t off = (((size_t)cr * p.H + h) * p.S_max + p0) * 128 * esz;
+                  const uint32_t bytes = (uint32_t)npos * 128 * esz;
+                  uint32_t s = acquire();
+                  uint32_t full = ptx::smem_u32(b_full + s);
+                  ptx::mbar_arrive_expect_tx(full, bytes);
+                  bulk_load(ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES), kbase + off, bytes, full);
+                  s = acquire();
+                  full = ptx::smem_u32(b_full + s);
+                  ptx::mbar_arrive_expect_tx(full, bytes);
+                  bulk_load(ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES), vbase + off, bytes, full);
+                }
+              }
+              unit0 += nch;
+            }
+          }
+        }
+        gemm_tiles(&tm_o, &tm_o, 1 << 30, s_o, l);
+        gemm_tiles(&tm_w1, &tm_w3, T1, s_w13, l);
+        gemm_tiles(&tm_w2, &tm_w2, 1 << 30, s_w2, l);
+      }
+      gemm_tiles(&tm_head, &tm_head, 1 << 30, s_head, 0);
+    }
+  } else if (warp == 1) {
+    // =================================== MMA ISSUER =================================================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, PC_NB);
+      uint32_t slot = 0, tile_ctr = 0, bphase = 0;
+      auto gemm_phase = [&](const PcSlice& sl) {
+        if (sl.nt == 0) return;
+        ptx::mbar_wait(ptx::smem_u32(b_ready), bphase & 1u);   // B operand of this phase staged
+        ++bphase;
+        ptx::tc_fence_after();
+        for (int i = 0; i < sl.nt; ++i) {
+          const uint32_t ab = tile_ctr & 1u, aph = (tile_ctr >> 1) & 1u;
+          ptx::mbar_wait(ptx::smem_u32(acc_empty + ab), aph ^ 1u);   // epilogue drained this accumulator
+          ptx::tc_fence_after();
+          const uint32_t dcol = tmem_base + ab * PC_NB;
+          for (int kb = sl.kb0; kb < sl.kb1; ++kb) {
+            const uint32_t s = slot % PC_STAGES, ph = (slot / PC_STAGES) & 1u;
+            ++slot;
+            ptx::mbar_wait(ptx::smem_u32(b_full + s), ph);
+            ptx::tc_fence_after();
+            const uint64_t ad = ptx::umma_desc_k_sw128(ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES));
+            const uint64_t bd = ptx::umma_desc_k_sw128(ptx::smem_u32(Bop + (size_t)(kb - sl.kb0) * (PC_NB * 128)));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16(dcol, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb != sl.kb0) || k != 0));
+            ptx::umma_commit(ptx::smem_u32(b_empty + s));
+          }
+          ptx::umma_commit(ptx::smem_u32(acc_full + ab));
+          ++tile_ctr;
+        }
+      };
+      bool waited = false;
+      for (int l = 0; l < p.n_layer; ++l) {
+        gemm_phase(s_qkv);
+        if (!waited) { pdl_wait(); waited = true; }
+        {  // skip the ring slots the attention units of this CTA consume
+          int unit0 = 0;
+          for (int r = 0; r < p.R; ++r) {
+            const int u = p.st.slot_map[r >> 1];
+            const int L = p.st.pos[u] + 1;
+            const int nch = att_chunks(L, ppc);
+            for (int h = 0; h < p.H; ++h) {
+              int first = (cta - (unit0 % G) + G) % G;
+              for (int c = first; c < nch; c += G)
+                if (min(L - 1, c * ppc + ppc) - c * ppc > 0) slot += 2;
+              unit0 += nch;
+            }
+          }
+        }
+        gemm_phase(s_o);
+        gemm_phase(s_w13);
+        gemm_phase(s_w2);
+      }
+      gemm_phase(s_head);
+    }
+  } else {
+    // =================================== COMPUTE WARPS ==============================================
+    const int ct = tid - 64;            // 0..127
+    const int cw = ct >> 5;             // 0..3
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may read
+    float* sm_o = sm_f;                 // [8][128]
+    float* sm_m = sm_f + 1024;          // [8]
+    float* sm_l = sm_m + 8;             // [8]
+    float* sm_rs = sm_l + 8;            // [PC_RPAD]
+    uint32_t slot = 0, tile_ctr = 0, bar_idx = 0;
+    pdl_wait();                         // state / x inputs of the previous kernels are visible
+
+    auto grid_arrive = [&]() {          // all compute threads have fenced their global writes
+      __threadfence();
+      compute_sync();
+      if (ct == 0) atomicAdd(p.bar, 1u);
+      ++bar_idx;
+    };
+    auto grid_wait = [&]() {            // wait for arrival #bar_idx of every CTA
+      if (ct == 0) {
+        const unsigned target = bar_idx * (unsigned)G;
+        const long long t0 = clock64();
+        while (ld_acquire_u32(p.bar) < target) {
+          if (clock64() - t0 > 4000000000ll) __trap();
+        }
+      }
+      compute_sync();
+    };
+    auto b_publish = [&]() {            // generic-proxy smem writes -> visible to the tensor core
+      fence_async_smem();
+      compute_sync();
+      if (ct == 0) ptx::mbar_arrive(ptx::smem_u32(b_ready));
+    };
+    // RMSNorm statistics of the R rows of x (fast_model.py:254-255): sm_rs[n] = rsqrt(mean(x^2) + eps)
+    auto row_rstd = [&]() {
+      for (int n = cw; n < p.R; n += 4) {
+        const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)n * p.D);
+        float ss = 0.f;
+        for (int i = lane; i < p.D / 4; i += 32) {
+          const float4 v = __ldcg(xr + i);
+          ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) sm_rs[n] = rsqrtf(ss / (float)p.D + p.eps);
+      }
+      compute_sync();
+    };
+    // B <- hi/lo split of (x * rstd) * gain over this CTA's K range
+    auto stage_norm = [&](const PcSlice& sl, const __nv_bfloat16* gain) {
+      if (sl.nt == 0) return;
+      row_rstd();
+      const int nchunk = (sl.kb1 - sl.kb0) * 8;
+      for (int i = ct; i < p.R * nchunk; i += 128) {
+        const int n = i / nchunk, c = i - n * nchunk;
+        const int k = sl.kb0 * 64 + c * 8;
+        const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)n * p.D + k);
+        const float4 a = __ldcg(xr), b = __ldcg(xr + 1);
+        const uint4 gw = *reinterpret_cast<const uint4*>(gain + k);
+        const float rs = sm_rs[n];
+        float v[8] = {(a.x * rs) * bf_lo(gw.x), (a.y * rs) * bf_hi(gw.x), (a.z * rs) * bf_lo(gw.y), (a.w * rs) * bf_hi(gw.y),
+                      (b.x * rs) * bf_lo(gw.z), (b.y * rs) * bf_hi(gw.z), (b.z * rs) * bf_lo(gw.w), (b.w * rs) * bf_hi(gw.w)};
+        b_store8(Bop, c >> 3, n, c & 7, v);
+      }
+      b_publish();
+    };
+    // epilogue of this CTA's tiles: TMEM -> red.add into out[n][col0 + row]
+    auto epilogue = [&](const PcSlice& sl, float* out, int ldo, int M, int split_t, float* out2) {
+      for (int i = 0; i < sl.nt; ++i) {
+        const int t = sl.t0 + i * sl.G;
+        const uint32_t ab = tile_ctr & 1u, aph = (tile_ctr >> 1) & 1u;
+        ++tile_ctr;
+        ptx::mbar_wait(ptx::smem_u32(acc_full + ab), aph);
+        ptx::tc_fence_after();
+        uint32_t hi[16], lo[16];
+        const uint32_t ta = tmem_base + ((uint32_t)(32 * quad) << 16) + ab * PC_NB;
+        ptx::tmem_ld16(ta, hi);
+        ptx::tmem_ld16(ta + PC_RPAD, lo);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(ptx::smem_u32(acc_empty + ab));
+        float* o = (t < split_t) ? out : out2;
+        const int j = ((t < split_t) ? t : t - split_t) * 128 + 32 * quad + lane;
+        if (j < M) {
+#pragma unroll
+          for (int n = 0; n < PC_RPAD; ++n)
+            if (n < p.R) atomicAdd(o + (size_t)n * ldo + j, __uint_as_float(hi[n]) + __uint_as_float(lo[n]));
+        }
+      }
+    };
+    auto zero_slice = [&](float* buf, size_t n_floats) {   // this CTA's share of a buffer
+      const size_t per = (n_floats / 4 + G - 1) / G;
+      const size_t b = (size_t)cta * per, e = min(n_floats / 4, b + per);
+      for (size_t i = b + ct; i < e; i += 128) reinterpret_cast<float4*>(buf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+
+    // ---- phase E: x = tok_emb + pos_emb + speaker (fast_model.py:152-157); CTA r builds row r
+    if (cta < p.R) {
+      const int u = p.st.slot_map[cta >> 1], c = cta & 1;
+      const __nv_bfloat16* te = p.tok_emb + (size_t)p.st.row_tok[2 * u + c] * p.D;
+      const __nv_bfloat16* pe = p.pos_emb + (size_t)p.st.pos[u] * p.D;
+      for (int d = ct; d < p.D; d += 128) {
+        float v = bf16_to_f32(te[d]) + bf16_to_f32(pe[d]);
+        if (c == 0) v += p.spk_proj[(size_t)u * p.D + d];
+        p.x[(size_t)cta * p.D + d] = v;
+      }
+    }
+    grid_arrive();
+
+    for (int l = 0; l < p.n_layer; ++l) {
+      const size_t lo_ = (size_t)l * p.layer_stride;
+      // ---- QKV: B = RMSNorm(x) * attn_norm; out: qkv (zero on entry)
+      grid_wait();
+      stage_norm(s_qkv, p.attn_norm + lo_);
+      epilogue(s_qkv, p.qkv, 3 * p.D, 3 * p.D, 1 << 30, nullptr);
+      slot += (uint32_t)(s_qkv.nt * (s_qkv.kb1 - s_qkv.kb0));
+      grid_arrive();
+
+      // ---- attention over [0, pos] + KV-cache append (fast_model.py:104-113, 220-224)
+      grid_wait();
+      zero_slice(p.gu, (size_t)PC_RPAD * 2 * p.F);
+      {
+        char* kbase = p.kv + (size_t)l * 2 * p.kv_half;
+        char* vbase = kbase + p.kv_half;
+        const int half = lane >> 4, sub = lane & 15;
+        int unit0 = 0;
+        for (int r = 0; r < p.R; ++r) {
+          const int u = p.st.slot_map[r >> 1];
+          const int cr = 2 * u + (r & 1);
+          const int L = p.st.pos[u] + 1;
+          const int nch = att_chunks(L, ppc);
+          for (int h = 0; h < p.H; ++h) {
+            int first = (cta - (unit0 % G) + G) % G;
+            for (int c = first; c < nch; c += G) {
+              const int p0 = c * ppc;
+              const int pend = min(L - 1, p0 + ppc);
+              const int npos = pend - p0;
+              const bool has_cur = (p0 + ppc >= L);   // this chunk owns the current position L-1
+              const float* qrow = p.qkv + (size_t)r * 3 * p.D + h * 128;
+              float q[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) q[i] = __ldcg(qrow + sub * 8 + i) * 0.08838834764831845f;
+              float m = -INFINITY, lsum = 0.f, o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = 0.f;
+              if (npos > 0) {
+                const uint32_t sk = slot % PC_STAGES, phk = (slot / PC_STAGES) & 1u;
+                const uint32_t sv = (slot + 1) % PC_STAGES, phv = ((slot + 1) / PC_STAGES) & 1u;
+                slot += 2;
+                ptx::mbar_wait(ptx::smem_u32(b_full + sk), phk);
+                ptx::mbar_wait(ptx::smem_u32(b_full + sv), phv);
+                const uint8_t* kt = ring + (size_t)sk * PC_STAGE_BYTES;
+                const uint8_t* vt = ring + (size_t)sv * PC_STAGE_BYTES;
+                for (int pb = cw * 2; pb < npos; pb += 8) {
+                  const int pp = pb + half;
+                  const bool valid = pp < npos;
+                  float kv[8], s = 0.f;
+                  if (valid) {
+                    load8s<KV_FP32>(kt, pp, sub, kv);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) s = fmaf(q[i], kv[i], s);
+                  }
+                  s += __shfl_xor_sync(0xffffffffu, s, 8);
+                  s += __shfl_xor_sync(0xffffffffu, s, 4);
+                  s += __shfl_xor_sync(0xffffffffu, s, 2);
+                  s += __shfl_xor_sync(0xffffffffu, s, 1);
+                  if (valid) {
+                    load8s<KV_FP32>(vt, pp, sub, kv);
+                    const float mn = fmaxf(m, s), corr = __expf(m - mn), pw = __expf(s - mn);
+                    lsum = lsum * corr + pw;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + pw * kv[i];
+                    m = mn;
+                  }
+                }
+                compute_sync();   // every warp is done with both tiles
+                if (ct == 0) {
+                  ptx::mbar_arrive(ptx::smem_u32(b_empty + sk));
+                  ptx::mbar_arrive(ptx::smem_u32(b_empty + sv));
+                }
+              }
+              if (has_cur) {
+                // the new token's k, v: complete sums from the qkv buffer, rounded like the cache stores them,
+                // appended to the cache and attended to by half-warp 0 of compute warp 0
+                const float* kc = p.qkv + (size_t)r * 3 * p.D + p.D + h * 128;
+                const float* vc = kc + p.D;
+                const float kval = __ldcg(kc + ct), vval = __ldcg(vc + ct);
+                const size_t e = (((size_t)cr * p.H + h) * p.S_max + (L - 1)) * 128 + ct;
+                if (KV_FP32) {
+                  reinterpret_cast<float*>(kbase)[e] = kval;
+                  reinterpret_cast<float*>(vbase)[e] = vval;
+                } else {
+                  reinterpret_cast<__nv_bfloat16*>(kbase)[e] = __float2bfloat16_rn(kval);
+                  reinterpret_cast<__nv_bfloat16*>(vbase)[e] = __float2bfloat16_rn(vval);
+                }
+                if (cw == 0) {
+                  float kv[8], s = 0.f;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float kk = __ldcg(kc + sub * 8 + i);
+                    kv[i] = KV_FP32 ? kk : __bfloat162float(__float2bfloat16_rn(kk));
+                    s = fmaf(q[i], kv[i], s);
+                  }
+                  s += __shfl_xor_sync(0xffffffffu, s, 8);
+                  s += __shfl_xor_sync(0xffffffffu, s, 4);
+                  s += __shfl_xor_sync(0xffffffffu, s, 2);
+                  s += __shfl_xor_sync(0xffffffffu, s, 1);
+                  if (half == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                      const float vv = __ldcg(vc + sub * 8 + i);
+                      kv[i] = KV_FP32 ? vv : __bfloat162float(__float2bfloat16_rn(vv));
+                    }
+                    const float mn = fmaxf(m, s), corr = __expf(m - mn), pw = __expf(s - mn);
+                    lsum = lsum * corr + pw;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + pw * kv[i];
+                    m = mn;
+                  }
+                }
+              }
+              // merge the 8 half-warp states -> one partial (m, l, o[128]) for this chunk
+              const int gidx = cw * 2 + half;
+              if (sub == 0) { sm_m[gidx] = m; sm_l[gidx] = lsum; }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) sm_o[gidx * 128 + sub * 8 + i] = o[i];
+              compute_sync();
+              {
+                float M = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) M = fmaxf(M, sm_m[i]);
+                float Ls = 0.f, O = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (sm_m[i] > -INFINITY) {
+                    const float w = __expf(sm_m[i] - M);
+                    Ls += sm_l[i] * w;
+                    O += sm_o[i * 128 + ct] * w;
+                  }
+                const size_t pidx = ((size_t)r * p.H + h) * PC_MAX_CHUNKS + c;
+                p.part_o[pidx * 128 + ct] = O;
+                if (ct == 0) { p.part_ml[pidx * 2] = M; p.part_ml[pidx * 2 + 1] = Ls; }
+              }
+              compute_sync();   // sm_o / sm_m are reused by the next unit
+            }
+            unit0 += nch;
+          }
+        }
+      }
+      grid_arrive();
+
+      // ---- wo + residual: B = merged attention output (columns = this CTA's K range of heads)
+      grid_wait();
+      zero_slice(p.qkv, (size_t)PC_RPAD * 3 * p.D);
+      if (s_o.nt > 0) {
+        const int nchunk = (s_o.kb1 - s_o.kb0) * 8;
+        for (int i = ct; i < p.R * nchunk; i += 128) {
+          const int n = i / nchunk, c = i - n * nchunk;
+          const int k = s_o.kb0 * 64 + c * 8;
+          const int h = k >> 7, d0 = k & 127;
+          const int u = p.st.slot_map[n >> 1];
+          const int nch = att_chunks(p.st.pos[u] + 1, ppc);
+          const size_t pb = ((size_t)n * p.H + h) * PC_MAX_CHUNKS;
+          float M = -INFINITY;
+          for (int z = 0; z < nch; ++z) M = fmaxf(M, __ldcg(p.part_ml + (pb + z) * 2));
+          float den = 0.f, v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+          for (int z = 0; z < nch; ++z) {
+            const float w = __expf(__ldcg(p.part_ml + (pb + z) * 2) - M);
+            den += __ldcg(p.part_ml + (pb + z) * 2 + 1) * w;
+            const float4* po = reinterpret_cast<const float4*>(p.part_o + (pb + z) * 128 + d0);
+            const float4 a = __ldcg(po), b = __ldcg(po + 1);
+            v[0] += a.x * w; v[1] += a.y * w; v[2] += a.z * w; v[3] += a.w * w;
+            v[4] += b.x * w; v[5] += b.y * w; v[6] += b.z * w; v[7] += b.w * w;
+          }
+          const float inv = 1.f / den;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] *= inv;
+          b_store8(Bop, c >> 3, n, c & 7, v);
+        }
+        b_publish();
+      }
+      epilogue(s_o, p.x, p.D, p.D, 1 << 30, nullptr);
+      slot += (uint32_t)(s_o.nt * (s_o.kb1 - s_o.kb0));
+      grid_arrive();
+
+      // ---- w1 | w3: B = RMSNorm(x) * ffn_norm; out: g | u (zero on entry)
+      grid_wait();
+      stage_norm(s_w13, p.ffn_norm + lo_);
+      epilogue(s_w13, p.gu, 2 * p.F, p.F, T1, p.gu + p.F);
+      slot += (uint32_t)(s_w13.nt * (s_w13.kb1 - s_w13.kb0));
+      grid_arrive();
+
+      // ---- w2 + residual: B = silu(g) * u (fast_model.py:237)
+      grid_wait();
+      if (s_w2.nt > 0) {
+        const int nchunk = (s_w2.kb1 - s_w2.kb0) * 8;
+        for (int i = ct; i < p.R * nchunk; i += 128) {
+          const int n = i / nchunk, c = i - n * nchunk;
+          const int k = s_w2.kb0 * 64 + c * 8;
+          const float4* gp = reinterpret_cast<const float4*>(p.gu + (size_t)n * 2 * p.F + k);
+          const float4* up = reinterpret_cast<const float4*>(p.gu + (size_t)n * 2 * p.F + p.F + k);
+          const float4 g0 = __ldcg(gp), g1 = __ldcg(gp + 1), u0 = __ldcg(up), u1 = __ldcg(up + 1);
+          const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = (g[e] / (1.f + expf(-g[e]))) * uu[e];
+          b_store8(Bop, c >> 3, n, c & 7, v);
+        }
+        b_publish();
+      }
+      epilogue(s_w2, p.x, p.D, p.D, 1 << 30, nullptr);
+      slot += (uint32_t)(s_w2.nt * (s_w2.kb1 - s_w2.kb0));
+      grid_arrive();
+    }
+    // ---- head: logits += RMSNorm(x) * out_norm . W_out^T   (rows n = batch order = sampler rows 2u, 2u+1)
+    grid_wait();
+    zero_slice(p.gu, (size_t)PC_RPAD * 2 * p.F);
+    stage_norm(s_head, p.out_norm);
+    epilogue(s_head, p.logits, p.V, p.V, 1 << 30, nullptr);
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 64);
+  }
+}
+
+}  // namespace mvb

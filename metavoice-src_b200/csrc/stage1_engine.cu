@@ -13,6 +13,7 @@
 #include "../../include/mvb200.h"
 #include "stage1_kernels.cuh"
 #include "umma_host.cuh"
+#include "decode_persistent.cuh"
 
 using namespace mvb;
 
@@ -54,6 +55,8 @@ struct WsLayout {
   size_t stage_idx, stage_spk, stage_forced;
   // path B (tensor-core rows path): activations for up to RB_MAX rows
   size_t b_x, b_qkv, b_att, b_ffn, b_logits, b_last, b_B, b_rows, b_scratch, b_tickets, b_part_o, b_part_ml, b_att_tickets;
+  // path C (persistent decode kernel)
+  size_t c_x, c_qkv, c_gu, c_part_o, c_part_ml, c_bar;
   size_t total;
 };
 
@@ -109,6 +112,12 @@ static WsLayout make_layout(const mvb_s1_config& c) {
     L.b_part_ml = take(RB * H * ATT_SPLITS * 2 * 4);
     L.b_att_tickets = take(RB * H * 4);
   }
+  L.c_x = take((size_t)PC_RPAD * D * 4);
+  L.c_qkv = take((size_t)PC_RPAD * 3 * D * 4);
+  L.c_gu = take((size_t)PC_RPAD * 2 * F * 4);
+  L.c_part_o = take((size_t)PC_RPAD * H * PC_MAX_CHUNKS * 128 * 4);
+  L.c_part_ml = take((size_t)PC_RPAD * H * PC_MAX_CHUNKS * 2 * 4);
+  L.c_bar = take(256);
   L.total = o;
   return L;
 }
@@ -136,6 +145,12 @@ struct mvb_s1 {
   int decode_b_min = 2;                               // utterances from which decode uses the tensor-core rows path
   int split_lo = 1;                                   // carry activations as hi+lo bf16 terms
   RowsDev rows;
+  // path C
+  bool path_c = true;
+  bool pc_ok = false;
+  CUtensorMap tm3[6];                                 // 3-D (k, row, layer) maps: wqkv, wo, w1, w3, w2, head
+  PcMat pm[5];
+  size_t layer_stride_elems = 0;
 
   template <typename T>
   T* wsp(size_t o) const { return reinterpret_cast<T*>(ws + o); }
@@ -146,6 +161,40 @@ struct mvb_s1 {
     return (size_t)2 * cfg.max_utts * cfg.n_head * cfg.block_size * cfg.head_dim * kv_elem();
   }
 };
+
+
+// 3-D tensor map over one matrix kind of every layer: dims {K, M, n_layer}, tile {64, 128, 1}, 128B swizzle.
+static bool make_tmap_bf16_3d(CUtensorMap* tm, const void* ptr, uint64_t K, uint64_t M, uint64_t L, uint64_t layer_stride_bytes) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {K, M, L};
+  cuuint64_t strides[2] = {K * 2, layer_stride_bytes};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Static decomposition of one matrix over `ctas` CTAs: the K split that minimises the busiest CTA's k-blocks.
+static PcMat plan_pc(int M, int K, int ctas) {
+  PcMat best{};
+  long best_cost = -1;
+  const int T = (M + 127) / 128, KB = K / 64;
+  for (int S = 1; S <= KB && S <= 16 && S <= ctas; ++S) {
+    const int Gp = ctas / S;
+    const int tiles_per = (T + Gp - 1) / Gp;
+    const int kb_per = (KB + S - 1) / S;
+    if (kb_per > PC_BKB_MAX) continue;
+    const long cost = (long)tiles_per * kb_per;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best.T = T; best.KB = KB; best.S = S; best.G = Gp;
+    }
+  }
+  if (best_cost < 0) best.S = 0;
+  return best;
+}
 
 static int validate(const mvb_s1_config* c) {
   if (!c) return fail(MVB_ERR_ARG, "null config");
@@ -229,6 +278,34 @@ extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size
     }
     ok = ok && make_tmap_bf16(&h->tmW[(size_t)cfg->n_layer * 5], h->w(4), cfg->vocab, D, 128);
     if (!ok) { delete h; return fail(MVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight matrix"); }
+  }
+  if (const char* e = getenv("MVB_PATHC")) h->path_c = atoi(e) != 0;
+  {
+    // persistent decode kernel: needs a uniform layer stride (true for arenas packed in checkpoint order)
+    const int D = cfg->dim, F = cfg->intermediate, V = cfg->vocab;
+    bool ok = cfg->n_layer >= 1;
+    const int o0 = MVB_S1_GLOBAL_TENSORS;
+    uint64_t stride = cfg->n_layer > 1 ? h->off[o0 + MVB_S1_LAYER_TENSORS] - h->off[o0] : 2 * (uint64_t)(4 * D * D + 3 * D * F + 2 * D);
+    for (int l = 1; l < cfg->n_layer && ok; ++l)
+      for (int t = 0; t < MVB_S1_LAYER_TENSORS; ++t)
+        ok = ok && (h->off[o0 + l * MVB_S1_LAYER_TENSORS + t] - h->off[o0 + (l - 1) * MVB_S1_LAYER_TENSORS + t] == stride);
+    ok = ok && (stride % 16 == 0);
+    h->layer_stride_elems = stride / 2;
+    const uint64_t NL = cfg->n_layer;
+    ok = ok && make_tmap_bf16_3d(&h->tm3[0], h->lw(0, 1), D, 3 * D, NL, stride);
+    ok = ok && make_tmap_bf16_3d(&h->tm3[1], h->lw(0, 2), D, D, NL, stride);
+    ok = ok && make_tmap_bf16_3d(&h->tm3[2], h->lw(0, 4), D, F, NL, stride);
+    ok = ok && make_tmap_bf16_3d(&h->tm3[3], h->lw(0, 5), D, F, NL, stride);
+    ok = ok && make_tmap_bf16_3d(&h->tm3[4], h->lw(0, 6), F, D, NL, stride);
+    ok = ok && make_tmap_bf16_3d(&h->tm3[5], h->w(4), D, V, 1, (uint64_t)V * D * 2);
+    h->pm[0] = plan_pc(3 * D, D, h->n_sm);
+    h->pm[1] = plan_pc(D, D, h->n_sm);
+    h->pm[2] = plan_pc(2 * F, D, h->n_sm);
+    h->pm[3] = plan_pc(D, F, h->n_sm);
+    h->pm[4] = plan_pc(V, D, h->n_sm);
+    for (int i = 0; i < 5; ++i) ok = ok && h->pm[i].S > 0;
+    ok = ok && (F % 128 == 0) && (D % 128 == 0);
+    h->pc_ok = ok;
   }
   CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
   CK(cudaMallocHost(&h->h_flags, sizeof(int) * 4 * 64));
@@ -423,6 +500,42 @@ static int launch_body_b(mvb_s1* h, cudaStream_t s, int n_utts) {
                                          h->wsp<float>(h->L.logits), c.vocab});
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Path C: one persistent kernel per decode position (decode_persistent.cuh) followed by the sampler.
+static int launch_persistent(mvb_s1* h, cudaStream_t s, int n_utts) {
+  const mvb_s1_config& c = h->cfg;
+  PcParams p{};
+  p.n_layer = c.n_layer; p.D = c.dim; p.F = c.intermediate; p.V = c.vocab; p.H = c.n_head; p.S_max = c.block_size;
+  p.R = 2 * n_utts; p.n_utts = n_utts; p.kv_fp32 = c.kv_dtype == MVB_KV_FP32; p.eps = c.norm_eps;
+  p.m_qkv = h->pm[0]; p.m_o = h->pm[1]; p.m_w13 = h->pm[2]; p.m_w2 = h->pm[3]; p.m_head = h->pm[4];
+  p.attn_norm = h->lw(0, 0); p.ffn_norm = h->lw(0, 3); p.out_norm = h->w(3);
+  p.layer_stride = h->layer_stride_elems;
+  p.tok_emb = h->w(0); p.pos_emb = h->w(1); p.spk_proj = h->wsp<float>(h->L.spk);
+  p.x = h->wsp<float>(h->L.c_x); p.qkv = h->wsp<float>(h->L.c_qkv); p.gu = h->wsp<float>(h->L.c_gu);
+  p.logits = h->wsp<float>(h->L.logits);
+  p.part_o = h->wsp<float>(h->L.c_part_o); p.part_ml = h->wsp<float>(h->L.c_part_ml);
+  p.kv = h->kv; p.kv_half = h->kv_half_bytes();
+  p.bar = h->wsp<unsigned>(h->L.c_bar);
+  p.st = h->st;
+  const size_t smem = 1024 + (size_t)PC_STAGES * PC_STAGE_BYTES + PC_B_BYTES + 25 * 8 + 16 + (1024 + 8 + 8 + PC_RPAD) * 4 + 64;
+  static bool attr_set[2] = {false, false};
+  const int fp = p.kv_fp32 ? 1 : 0;
+  if (!attr_set[fp]) {
+    if (fp) CK(cudaFuncSetAttribute(k_decode_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else CK(cudaFuncSetAttribute(k_decode_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[fp] = true;
+  }
+  h->launches++;
+  if (fp)
+    CK(launch_pdl(h->pdl, k_decode_persistent<true>, dim3(h->n_sm), dim3(PC_THREADS), smem, s, h->tm3[0], h->tm3[1], h->tm3[2],
+                  h->tm3[3], h->tm3[4], h->tm3[5], p));
+  else
+    CK(launch_pdl(h->pdl, k_decode_persistent<false>, dim3(h->n_sm), dim3(PC_THREADS), smem, s, h->tm3[0], h->tm3[1], h->tm3[2],
+                  h->tm3[3], h->tm3[4], h->tm3[5], p));
+  return MVB_OK;
+}
+
 static int run_body(mvb_s1* h, cudaStream_t s, int n_utts, bool allow_b = true) {
   // Path A (CUDA-core GEMV) streams the weights once per utterance; from 2 utterances up the tensor-core
   // rows path streams them once per step for the whole batch.  slot_map must be the identity for path B
@@ -567,9 +680,9 @@ static int sample_step(mvb_s1* h, cudaStream_t s, int n_utts) {
   sp.logits = h->wsp<float>(h->L.logits);
   sp.V = h->cfg.vocab;
   sp.decode_mode = 1;
-  k_sample<<<n_utts, SAMP_THREADS, 0, s>>>(sp, h->st);
+  sp.grid_bar = h->wsp<unsigned>(h->L.c_bar);
   h->launches++;
-  CK(cudaGetLastError());
+  CK(launch_pdl(h->pdl, k_sample, dim3(n_utts), dim3(SAMP_THREADS), 0, s, sp, h->st));
   return MVB_OK;
 }
 
@@ -580,10 +693,37 @@ extern "C" int mvb_s1_decode(mvb_s1* h, int32_t n_utts, int32_t n_steps, void* s
   k_identity_slots<<<1, 64, 0, s>>>(h->st, n_utts);
   h->launches++;
   CK(cudaGetLastError());
+  const bool use_c = h->path_c && h->pc_ok && 2 * n_utts <= PC_RPAD;
   for (int i = 0; i < n_steps; ++i) {
-    if (int e = run_body(h, s, n_utts)) return e;
+    if (use_c) {
+      if (int e = launch_persistent(h, s, n_utts)) return e;
+    } else {
+      if (int e = run_body(h, s, n_utts)) return e;
+    }
     if (int e = sample_step(h, s, n_utts)) return e;
   }
+  return MVB_OK;
+}
+
+
+// Parity hook for the persistent decode kernel: one fused position for utterances [0, n_utts) from the current
+// decode state (tokens/positions installed with mvb_s1_begin), logits copied out, no sampling, state untouched
+// except for the KV-cache append at the current positions.
+extern "C" int mvb_s1_step_logits(mvb_s1* h, int32_t n_utts, float* d_logits, void* stream) {
+  if (!h || !d_logits) return fail(MVB_ERR_ARG, "null argument");
+  if (n_utts < 1 || n_utts > h->cfg.max_utts || 2 * n_utts > PC_RPAD) return fail(MVB_ERR_ARG, "n_utts %d out of range", n_utts);
+  if (!h->pc_ok) return fail(MVB_ERR_UNSUPPORTED, "persistent decode kernel unavailable for this configuration");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t bytes = sizeof(float) * 2 * (size_t)n_utts * h->cfg.vocab;
+  k_identity_slots<<<1, 64, 0, s>>>(h->st, n_utts);
+  h->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemsetAsync(h->wsp<float>(h->L.logits), 0, bytes, s));
+  CK(cudaMemsetAsync(h->wsp<unsigned>(h->L.c_bar), 0, 4, s));
+  if (int e = launch_persistent(h, s, n_utts)) return e;
+  CK(cudaMemcpyAsync(d_logits, h->wsp<float>(h->L.logits), bytes, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemsetAsync(h->wsp<float>(h->L.logits), 0, bytes, s));
+  CK(cudaMemsetAsync(h->wsp<unsigned>(h->L.c_bar), 0, 4, s));
   return MVB_OK;
 }
 

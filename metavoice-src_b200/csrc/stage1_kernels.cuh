@@ -491,6 +491,7 @@ struct SampleP {
   unsigned long long step;
   int* token_out;
   float* probs_out;
+  unsigned* grid_bar;  // decode mode: arrival counter of the persistent decode kernel, reset here between steps
 };
 
 __global__ void __launch_bounds__(SAMP_THREADS) k_sample(SampleP p, S1State st) {
@@ -501,6 +502,9 @@ __global__ void __launch_bounds__(SAMP_THREADS) k_sample(SampleP p, S1State st) 
   __shared__ unsigned long long s_best[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = p.V;
+  pdl_launch_dependents();   // the next decode kernel may start prefetching weights while we sample
+  pdl_wait();                // logits of this step are complete
+  if (p.decode_mode && p.grid_bar && blockIdx.x == 0 && tid == 0) *p.grid_bar = 0u;
   int u = 0;
   SamplingDev sp = p.sp;
   const float* noise = p.noise;
@@ -524,6 +528,11 @@ __global__ void __launch_bounds__(SAMP_THREADS) k_sample(SampleP p, S1State st) 
     if (v < V) k = __fdiv_rn(__fadd_rn(__fmul_rn(g, lc[v]), __fmul_rn(omg, lu[v])), tdiv);
     key[v] = k;
     sid[v] = (unsigned short)v;
+  }
+  if (p.decode_mode) {
+    // the persistent decode kernel accumulates split-K partial logits with red.add: hand the rows back zeroed
+    float* z = const_cast<float*>(lc);
+    for (int v = tid; v < 2 * V; v += SAMP_THREADS) z[v] = 0.f;
   }
   __syncthreads();
 

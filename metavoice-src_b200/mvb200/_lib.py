@@ -46,6 +46,7 @@ SIGNATURES = {
                                C.c_void_p, C.c_void_p]),
     "mvb_s1_fetch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32),
                                C.POINTER(C.c_int32), C.c_void_p]),
+    "mvb_s1_step_logits": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "mvb_s1_launch_count": (C.c_uint64, [C.c_void_p]),
     "mvb_linear": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_float,
                              C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),

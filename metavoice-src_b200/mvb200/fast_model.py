@@ -161,19 +161,24 @@ class Transformer:
         h = C.c_void_p()
         torch.cuda.synchronize(self.device)
         import os
-        prev = os.environ.get("MVB_PATHB")
+        # test hook: True/"BC" = all engine paths, False/"" = CUDA-core kernels only, "B" = tensor-core rows path
+        # without the persistent decode kernel, "C" = persistent decode kernel with CUDA-core prefill
+        saved = {k: os.environ.get(k) for k in ("MVB_PATHB", "MVB_PATHC")}
         if tensor_core_path is not None:
-            os.environ["MVB_PATHB"] = "1" if tensor_core_path else "0"
+            paths = ("BC" if tensor_core_path else "") if isinstance(tensor_core_path, bool) else str(tensor_core_path)
+            os.environ["MVB_PATHB"] = "1" if "B" in paths else "0"
+            os.environ["MVB_PATHC"] = "1" if "C" in paths else "0"
         try:
             with torch.cuda.device(self.device):
                 rc = self._lib.mvb_s1_create(C.byref(cfg), self._arena.data_ptr(), self._arena.numel(), offs,
                                              self._kv.data_ptr(), self._ws.data_ptr(), C.byref(h))
         finally:
             if tensor_core_path is not None:
-                if prev is None:
-                    os.environ.pop("MVB_PATHB", None)
-                else:
-                    os.environ["MVB_PATHB"] = prev
+                for k, v in saved.items():
+                    if v is None:
+                        os.environ.pop(k, None)
+                    else:
+                        os.environ[k] = v
         _lib.check(rc)
         self._handle = h
         self._spk_key = None

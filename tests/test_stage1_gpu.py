@@ -215,9 +215,70 @@ def test_batched_decode_tensor_core_path_equals_cuda_core_path(tiny_sd):
     n_new = 16
     noise = torch.empty(4, n_new, d.vocab_size).exponential_(1, generator=torch.Generator().manual_seed(6))
     out = {}
-    for tc in (False, True):
+    for tc in ("", "B", "BC"):   # CUDA-core kernels only / tcgen05 rows path / + persistent fused decode kernel
         m = _mk(d, tiny_sd, "fp32", utts=4, tc=tc)
         out[tc] = U.generate_batch(m, prompts, spk, max_new_tokens=n_new, end_of_audio_token=9999, noise=noise,
                                    guidance_scale=3.0, temperature=1.0, top_p=0.95)
-    for a, b in zip(out[False], out[True]):
-        assert a.tolist() == b.tolist() and len(a) == n_new
+    for a, b, c in zip(out[""], out["B"], out["BC"]):
+        assert a.tolist() == b.tolist() == c.tolist() and len(a) == n_new
+
+
+def _persistent_steps(model, spk, prompt, tokens, n_steps):
+    """Prefill, then teacher-forced decode positions through the persistent fused kernel; returns logits per step."""
+    import ctypes as C
+    from mvb200 import _lib
+    T = prompt.numel()
+    idx = prompt.view(1, -1).repeat(2, 1).cuda()
+    out = [model(idx, spk.cuda(), torch.arange(T))[:, -1].cpu()]
+    lib, h, st = model._lib, model.handle, model._stream()
+    sp = _lib.Sampling(3.0, 1.0, 0.95, 0, 9999, 1)
+    for s in range(1, n_steps + 1):
+        _lib.check(lib.mvb_s1_begin(h, 0, int(tokens[s - 1]), T + s - 1, C.byref(sp), None, None, st))
+        lg = torch.empty(2, model.config.vocab_size, device="cuda")
+        _lib.check(lib.mvb_s1_step_logits(h, 1, lg.data_ptr(), st))
+        out.append(lg.cpu())
+    return out
+
+
+def test_persistent_kernel_logits_tiny_vs_reference_golden(golden_dir, tiny_sd):
+    g = _golden(golden_dir, "stage1_tiny")
+    for kv, tol in (("fp32", TOL), ("bf16", None)):
+        m = _mk(synth.TINY, tiny_sd, kv)
+        steps = [int(s) for s in g["steps"]]
+        lg = _persistent_steps(m, torch.from_numpy(g["spk"]), torch.from_numpy(g["prompt"]), g["tokens"], max(steps))
+        for i, s in enumerate(steps):
+            ref32 = torch.from_numpy(g["logits"][i])
+            err = _rel(lg[s], ref32)
+            print(f"persistent kernel tiny kv={kv} step {s}: rel err {err:.2e}")
+            bound = tol if tol else _rel(torch.from_numpy(g["logits_ref_bf16"][i]), ref32)
+            assert err < bound
+
+
+def test_persistent_kernel_logits_full_vs_reference_golden(golden_dir, full_sd):
+    g = _golden(golden_dir, "stage1_full")
+    m = _mk(synth.FULL, full_sd, "fp32")
+    steps = [int(s) for s in g["steps"]]
+    lg = _persistent_steps(m, torch.from_numpy(g["spk"]), torch.from_numpy(g["prompt"]), g["tokens"], max(steps))
+    errs = [_rel(lg[s], torch.from_numpy(g["logits"][i])) for i, s in enumerate(steps)]
+    print("persistent kernel, 1.2B, fp32 KV, rel err per step", errs)
+    assert max(errs) < TOL
+
+
+def test_full_generate_reproduces_reference_tokens(golden_dir, full_sd):
+    """End to end on the 1.2 B configuration: tensor-core prefill + persistent decode kernel + sampler, fed the
+    Exp(1) stream the reference consumed (same seed, same call order) -> the reference's own 65 token ids."""
+    from mvb200 import fast_inference_utils as U
+    g = _golden(golden_dir, "stage1_full")
+    n = len(g["tokens"]); V = synth.FULL.vocab_size
+    torch.manual_seed(1337)
+    noise = torch.stack([torch.empty(V).exponential_(1) for _ in range(n)])
+    for i, s in enumerate(g["steps"]):
+        assert torch.equal(noise[int(s)], torch.from_numpy(g["noise"][i]))
+    m = _mk(synth.FULL, full_sd, "fp32")
+    y = U.generate(m, torch.from_numpy(g["prompt"]), torch.from_numpy(g["spk"]), max_new_tokens=n,
+                   end_of_audio_token=9999, noise=noise, guidance_scale=float(g["guidance"]),
+                   temperature=float(g["temperature"]), top_p=float(g["top_p"]))
+    got = y[len(g["prompt"]):].tolist()
+    same = sum(int(a == b) for a, b in zip(got, g["tokens"].tolist()))
+    print(f"1.2B generate: {same}/{n} token ids identical to the reference")
+    assert got == g["tokens"].tolist()
