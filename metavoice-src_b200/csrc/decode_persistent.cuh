@@ -30,6 +30,7 @@ constexpr int PC_BKB_MAX = 12;       // k-blocks of B one CTA may own in a phase
 constexpr int PC_B_BYTES = PC_BKB_MAX * PC_NB * 128;
 constexpr int PC_ATT_CHUNK_BYTES = PC_STAGE_BYTES;  // one KV tile = one ring stage
 constexpr int PC_MAX_CHUNKS = 64;    // per (row, head): ceil(2048 / 32) in fp32 mode
+constexpr int PC_TRACE_EVENTS = 512;
 
 struct PcMat {     // one weight matrix kind, static decomposition
   int T;           // row tiles (of 128)
@@ -58,6 +59,7 @@ struct PcParams {
   char* kv;
   size_t kv_half;  // bytes of one layer's K (or V) region
   unsigned* bar;   // grid-wide arrival counter (zero at launch)
+  long long* trace;  // optional [gridDim][PC_TRACE_EVENTS] clock64 stamps of compute-thread 0 (debug)
   S1State st;
 };
 
@@ -324,6 +326,12 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     float* sm_rs = sm_l + 8;            // [PC_RPAD]
     uint32_t slot = 0, tile_ctr = 0, bar_idx = 0;
     pdl_wait();                         // state / x inputs of the previous kernels are visible
+    int ev = 0;
+    auto stamp = [&]() {
+      if (p.trace != nullptr && ct == 0 && ev < PC_TRACE_EVENTS) p.trace[(size_t)cta * PC_TRACE_EVENTS + ev] = clock64();
+      ++ev;
+    };
+    stamp();
 
     auto grid_arrive = [&]() {          // all compute threads have fenced their global writes
       __threadfence();
@@ -419,19 +427,24 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         p.x[(size_t)cta * p.D + d] = v;
       }
     }
+    stamp();
     grid_arrive();
 
     for (int l = 0; l < p.n_layer; ++l) {
       const size_t lo_ = (size_t)l * p.layer_stride;
       // ---- QKV: B = RMSNorm(x) * attn_norm; out: qkv (zero on entry)
       grid_wait();
+      stamp();
       stage_norm(s_qkv, p.attn_norm + lo_);
+      stamp();
       epilogue(s_qkv, p.qkv, 3 * p.D, 3 * p.D, 1 << 30, nullptr);
       slot += (uint32_t)(s_qkv.nt * (s_qkv.kb1 - s_qkv.kb0));
+      stamp();
       grid_arrive();
 
       // ---- attention over [0, pos] + KV-cache append (fast_model.py:104-113, 220-224)
       grid_wait();
+      stamp();
       zero_slice(p.gu, (size_t)PC_RPAD * 2 * p.F);
       {
         char* kbase = p.kv + (size_t)l * 2 * p.kv_half;
@@ -561,10 +574,12 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           }
         }
       }
+      stamp();
       grid_arrive();
 
       // ---- wo + residual: B = merged attention output (columns = this CTA's K range of heads)
       grid_wait();
+      stamp();
       zero_slice(p.qkv, (size_t)PC_RPAD * 3 * p.D);
       if (s_o.nt > 0) {
         const int nchunk = (s_o.kb1 - s_o.kb0) * 8;
@@ -595,19 +610,25 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         }
         b_publish();
       }
+      stamp();
       epilogue(s_o, p.x, p.D, p.D, 1 << 30, nullptr);
       slot += (uint32_t)(s_o.nt * (s_o.kb1 - s_o.kb0));
+      stamp();
       grid_arrive();
 
       // ---- w1 | w3: B = RMSNorm(x) * ffn_norm; out: g | u (zero on entry)
       grid_wait();
+      stamp();
       stage_norm(s_w13, p.ffn_norm + lo_);
+      stamp();
       epilogue(s_w13, p.gu, 2 * p.F, p.F, T1, p.gu + p.F);
       slot += (uint32_t)(s_w13.nt * (s_w13.kb1 - s_w13.kb0));
+      stamp();
       grid_arrive();
 
       // ---- w2 + residual: B = silu(g) * u (fast_model.py:237)
       grid_wait();
+      stamp();
       if (s_w2.nt > 0) {
         const int nchunk = (s_w2.kb1 - s_w2.kb0) * 8;
         for (int i = ct; i < p.R * nchunk; i += 128) {
@@ -625,15 +646,20 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         }
         b_publish();
       }
+      stamp();
       epilogue(s_w2, p.x, p.D, p.D, 1 << 30, nullptr);
       slot += (uint32_t)(s_w2.nt * (s_w2.kb1 - s_w2.kb0));
+      stamp();
       grid_arrive();
     }
     // ---- head: logits += RMSNorm(x) * out_norm . W_out^T   (rows n = batch order = sampler rows 2u, 2u+1)
     grid_wait();
     zero_slice(p.gu, (size_t)PC_RPAD * 2 * p.F);
+    stamp();
     stage_norm(s_head, p.out_norm);
+    stamp();
     epilogue(s_head, p.logits, p.V, p.V, 1 << 30, nullptr);
+    stamp();
     ptx::tc_fence_before();
   }
   __syncthreads();

@@ -56,7 +56,7 @@ struct WsLayout {
   // path B (tensor-core rows path): activations for up to RB_MAX rows
   size_t b_x, b_qkv, b_att, b_ffn, b_logits, b_last, b_B, b_rows, b_scratch, b_tickets, b_part_o, b_part_ml, b_att_tickets;
   // path C (persistent decode kernel)
-  size_t c_x, c_qkv, c_gu, c_part_o, c_part_ml, c_bar;
+  size_t c_x, c_qkv, c_gu, c_part_o, c_part_ml, c_bar, c_trace;
   size_t total;
 };
 
@@ -118,6 +118,7 @@ static WsLayout make_layout(const mvb_s1_config& c) {
   L.c_part_o = take((size_t)PC_RPAD * H * PC_MAX_CHUNKS * 128 * 4);
   L.c_part_ml = take((size_t)PC_RPAD * H * PC_MAX_CHUNKS * 2 * 4);
   L.c_bar = take(256);
+  L.c_trace = take((size_t)160 * PC_TRACE_EVENTS * 8);
   L.total = o;
   return L;
 }
@@ -148,6 +149,7 @@ struct mvb_s1 {
   // path C
   bool path_c = true;
   bool pc_ok = false;
+  bool trace = false;
   CUtensorMap tm3[6];                                 // 3-D (k, row, layer) maps: wqkv, wo, w1, w3, w2, head
   PcMat pm[5];
   size_t layer_stride_elems = 0;
@@ -280,6 +282,7 @@ extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size
     if (!ok) { delete h; return fail(MVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight matrix"); }
   }
   if (const char* e = getenv("MVB_PATHC")) h->path_c = atoi(e) != 0;
+  if (const char* e = getenv("MVB_PC_TRACE")) h->trace = atoi(e) != 0;
   {
     // persistent decode kernel: needs a uniform layer stride (true for arenas packed in checkpoint order)
     const int D = cfg->dim, F = cfg->intermediate, V = cfg->vocab;
@@ -517,6 +520,7 @@ static int launch_persistent(mvb_s1* h, cudaStream_t s, int n_utts) {
   p.part_o = h->wsp<float>(h->L.c_part_o); p.part_ml = h->wsp<float>(h->L.c_part_ml);
   p.kv = h->kv; p.kv_half = h->kv_half_bytes();
   p.bar = h->wsp<unsigned>(h->L.c_bar);
+  p.trace = (h->trace && h->n_sm <= 160) ? h->wsp<long long>(h->L.c_trace) : nullptr;
   p.st = h->st;
   const size_t smem = 1024 + (size_t)PC_STAGES * PC_STAGE_BYTES + PC_B_BYTES + 25 * 8 + 16 + (1024 + 8 + 8 + PC_RPAD) * 4 + 64;
   static bool attr_set[2] = {false, false};
@@ -725,6 +729,16 @@ extern "C" int mvb_s1_step_logits(mvb_s1* h, int32_t n_utts, float* d_logits, vo
   CK(cudaMemsetAsync(h->wsp<float>(h->L.logits), 0, bytes, s));
   CK(cudaMemsetAsync(h->wsp<unsigned>(h->L.c_bar), 0, 4, s));
   return MVB_OK;
+}
+
+// Debug: copy the persistent kernel's per-CTA phase time stamps (clock64) of the last step to the host.
+extern "C" int mvb_s1_trace_fetch(mvb_s1* h, long long* out, int32_t max_ctas, void* stream) {
+  if (!h || !out) return fail(MVB_ERR_ARG, "null argument");
+  const int n = h->n_sm < max_ctas ? h->n_sm : max_ctas;
+  CK(cudaMemcpyAsync(out, h->wsp<long long>(h->L.c_trace), sizeof(long long) * (size_t)n * PC_TRACE_EVENTS, cudaMemcpyDeviceToHost,
+                     (cudaStream_t)stream));
+  CK(cudaStreamSynchronize((cudaStream_t)stream));
+  return n;
 }
 
 extern "C" int mvb_s1_fetch(mvb_s1* h, int32_t utt, int32_t* out_tokens, int32_t cap, int32_t* n_out, int32_t* done,

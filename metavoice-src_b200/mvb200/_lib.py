@@ -54,6 +54,7 @@ SIGNATURES = {
 # helper exported for the parity tests only (not part of the drop-in surface)
 TEST_SIGNATURES = {
     "mvb_s1_fetch_sampled": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "mvb_s1_trace_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 
 _lib = None

@@ -27,10 +27,11 @@ res = []
 for item in spec.split(","):
     kind, n = item.split(":")
     n = int(n)
-    os.environ["MVB_PDL"] = "0" if kind == "A0" else "1"
+    os.environ["MVB_PDL"] = "0" if kind.endswith("0") else "1"
     os.environ["MVB_DECODE_B_MIN"] = "1" if kind.startswith("B") else "9999"
+    os.environ["MVB_PATHC"] = "1" if kind.startswith("C") else "0"
     m = Transformer(cfg, arena, offsets, device=dev)
-    m.setup_caches(2 * n, cfg.block_size, kv_dtype="bf16", tensor_core_path=True)
+    m.setup_caches(2 * n, cfg.block_size, kv_dtype="bf16")
     lib, h, st = m._lib, m.handle, m._stream()
     for u in range(n):
         sp = _lib.Sampling(3.0, 1.0, 0.95, 0, 9999, 5 + u)
