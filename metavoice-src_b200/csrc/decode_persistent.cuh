@@ -3,16 +3,17 @@
 //   * grid = one CTA per SM; every CTA owns a static slice of every weight matrix:
 //       (K split s = cta % S, row tiles t = cta / S, + groups, ...)  chosen per matrix on the host.
 //   * warp 0 = PRODUCER: one thread walks the whole step's byte schedule -- weight tiles via TMA
-//     (cp.async.bulk.tensor, 128B swizzle) and KV-cache tiles via cp.async.bulk -- into a ring of 16 KB smem
-//     stages guarded by full/empty mbarriers.  Weights and old KV do not depend on this step's activations,
-//     so the producer never waits for a grid barrier: the HBM stream keeps running across phase boundaries.
-//   * warp 1 = MMA ISSUER: one thread issues tcgen05.mma (M=128 weight rows x N=32 activation columns,
-//     fp32 accumulators double-buffered in TMEM) straight from the ring; activations are the exact
-//     hi+lo bf16 split of the fp32 vectors, so products match fp32-activation math to ~1e-5.
-//   * warps 2..5 = COMPUTE: wait for the previous phase grid-wide (split arrive/wait counter), stage the
-//     B operand into swizzled smem (RMSNorm / attention-merge / SiLU*mul fused here), run the epilogues
-//     (tcgen05.ld -> red.global.add.f32 split-K accumulation) and the decode attention on smem KV tiles
-//     (online softmax per half-warp).
+//     (cp.async.bulk.tensor, 128B swizzle) into a ring of 16 KB smem stages, KV-cache tiles via cp.async.bulk
+//     into two dedicated (K,V) tile slots -- all guarded by full/empty mbarriers.  Weights and old KV do not
+//     depend on this step's activations, so the producer never waits for a grid barrier: the HBM stream keeps
+//     running across phase boundaries, and a layer's first KV tiles are in flight before its QKV GEMM starts.
+//   * warp 1 = MMA ISSUER: one thread issues tcgen05.mma (M=128 weight rows x N activation columns, fp32
+//     accumulators double-buffered in TMEM) straight from the ring; activations are the exact hi+lo bf16
+//     split of the fp32 vectors (N = 16: 8 rows, N = 32: 16 rows), so products match fp32-activation math to ~1e-5.
+//   * warps 2..5 = COMPUTE: wait for the previous phase grid-wide (split arrive/wait counter with
+//     release/acquire atomics), stage the B operand into swizzled smem (RMSNorm / attention-merge / SiLU*mul
+//     fused here), run the epilogues (tcgen05.ld -> red.global.add.f32 split-K accumulation) and the decode
+//     attention on smem KV tiles (online softmax per half-warp).
 //   * phases per layer: QKV | attention (+KV-cache append) | wo+residual | w1,w3 | w2+residual, then head.
 //     5 grid-wide dependencies per layer, no host involvement, no per-layer launch.
 #pragma once
@@ -22,15 +23,21 @@
 namespace mvb {
 
 constexpr int PC_THREADS = 192;      // producer warp + MMA warp + 4 compute warps
-constexpr int PC_STAGES = 10;        // ring depth (x 16 KB)
 constexpr int PC_STAGE_BYTES = 16384;
-constexpr int PC_NB = 32;            // UMMA N: 16 hi rows + 16 lo rows
-constexpr int PC_RPAD = 16;          // max activation rows (8 utterances x 2 CFG rows)
+constexpr int PC_RPAD = 16;          // rows of the fp32 activation buffers (8 utterances x 2 CFG rows)
 constexpr int PC_BKB_MAX = 12;       // k-blocks of B one CTA may own in a phase
-constexpr int PC_B_BYTES = PC_BKB_MAX * PC_NB * 128;
-constexpr int PC_ATT_CHUNK_BYTES = PC_STAGE_BYTES;  // one KV tile = one ring stage
+constexpr int PC_NKV = 2;            // (K tile, V tile) slots
 constexpr int PC_MAX_CHUNKS = 64;    // per (row, head): ceil(2048 / 32) in fp32 mode
 constexpr int PC_TRACE_EVENTS = 512;
+
+template <int NB> struct PcCfg {
+  static constexpr int STAGES = (NB == 16) ? 8 : 6;
+  static constexpr int B_BYTES = PC_BKB_MAX * NB * 128;
+  static constexpr int RH = NB / 2;                      // activation rows carried (hi rows; lo rows follow)
+  static constexpr int TMEM_COLS = (2 * NB < 32) ? 32 : 2 * NB;
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * PC_STAGE_BYTES + B_BYTES + (size_t)PC_NKV * 2 * PC_STAGE_BYTES +
+                                 (2 * STAGES + 1 + 4 + 2 * PC_NKV) * 8 + 16 + (1024 + 8 + 8 + PC_RPAD + 256 + 64) * 4 + 64;
+};
 
 struct PcMat {     // one weight matrix kind, static decomposition
   int T;           // row tiles (of 128)
@@ -69,6 +76,9 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void red_release_inc(unsigned* p) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -84,11 +94,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
 
 // byte offset of the 16-byte chunk holding k..k+7 of activation row `row` inside the B operand
 // (K-major, 128B swizzle, [k-block][NB rows][128 B])
+template <int NB>
 __device__ __forceinline__ uint32_t b_chunk_off(int kb_local, int row, int kchunk /* (k % 64) / 8 */) {
-  return (uint32_t)(kb_local * (PC_NB * 128) + (row >> 3) * 1024 + (row & 7) * 128 + ((kchunk ^ (row & 7)) << 4));
+  return (uint32_t)(kb_local * (NB * 128) + (row >> 3) * 1024 + (row & 7) * 128 + ((kchunk ^ (row & 7)) << 4));
 }
 
 // split 8 fp32 into bf16 hi / lo and store both rows' chunks
+template <int NB>
 __device__ __forceinline__ void b_store8(uint8_t* B, int kb_local, int n, int kchunk, const float (&v)[8]) {
   uint32_t hi[4], lo[4];
 #pragma unroll
@@ -99,8 +111,8 @@ __device__ __forceinline__ void b_store8(uint8_t* B, int kb_local, int n, int kc
     hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
     lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
   }
-  *reinterpret_cast<uint4*>(B + b_chunk_off(kb_local, n, kchunk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(B + b_chunk_off(kb_local, PC_RPAD + n, kchunk)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  *reinterpret_cast<uint4*>(B + b_chunk_off<NB>(kb_local, n, kchunk)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(B + b_chunk_off<NB>(kb_local, NB / 2 + n, kchunk)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 struct PcSlice {   // what this CTA owns of one matrix
@@ -117,13 +129,27 @@ __device__ __forceinline__ PcSlice pc_slice(const PcMat& m, int cta) {
   return s;
 }
 
-// attention work list of this CTA: units (row, head, chunk) round-robin over CTAs
-struct PcAtt {
-  int pos_per_chunk;   // positions per 16 KB tile
-  int total;           // units in this layer
-};
-
 __device__ __forceinline__ int att_chunks(int L, int ppc) { return (L + ppc - 1) / ppc; }
+
+// Enumerates this CTA's attention units of one layer in a fixed order: unit = (row r, head h, chunk c), global
+// unit ids are dealt round-robin to CTAs.  Producer and compute warps walk the identical sequence.
+struct AttIter {
+  int r, h, c, unit0, L, nch, cr;
+};
+template <typename F>
+__device__ __forceinline__ void for_each_att_unit(const PcParams& p, int cta, int G, int ppc, F&& f) {
+  int unit0 = 0;
+  for (int r = 0; r < p.R; ++r) {
+    const int u = p.st.slot_map[r >> 1];
+    const int L = p.st.pos[u] + 1;
+    const int nch = att_chunks(L, ppc);
+    for (int h = 0; h < p.H; ++h) {
+      const int first = (cta - (unit0 % G) + G) % G;
+      for (int c = first; c < nch; c += G) f(r, h, c, L, 2 * u + (r & 1));
+      unit0 += nch;
+    }
+  }
+}
 
 template <bool KV_FP32>
 __device__ __forceinline__ void load8s(const uint8_t* tile, int p, int sub, float (&v)[8]) {
@@ -138,33 +164,38 @@ __device__ __forceinline__ void load8s(const uint8_t* tile, int p, int sub, floa
   }
 }
 
-template <bool KV_FP32>
+template <bool KV_FP32, int NB>
 __global__ void __launch_bounds__(PC_THREADS, 1)
 k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_o,
                     const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w3,
                     const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_head,
                     const PcParams p) {
+  using Cfg = PcCfg<NB>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int RH = Cfg::RH;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* ring = smem;
-  uint8_t* Bop = smem + PC_STAGES * PC_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Bop + PC_B_BYTES);
-  // bars: full[S] empty[S] b_ready acc_full[2] acc_empty[2]
+  uint8_t* Bop = ring + STAGES * PC_STAGE_BYTES;
+  uint8_t* kvbuf = Bop + Cfg::B_BYTES;                       // [NKV][K tile | V tile]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(kvbuf + PC_NKV * 2 * PC_STAGE_BYTES);
   uint64_t* b_full = bars;
-  uint64_t* b_empty = bars + PC_STAGES;
-  uint64_t* b_ready = bars + 2 * PC_STAGES;
+  uint64_t* b_empty = b_full + STAGES;
+  uint64_t* b_ready = b_empty + STAGES;
   uint64_t* acc_full = b_ready + 1;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* sm_f = reinterpret_cast<float*>(tmem_slot + 4);   // [8][128] o, [8] m, [8] l, [PC_RPAD] rstd  (compute scratch)
+  uint64_t* kv_full = acc_empty + 2;
+  uint64_t* kv_empty = kv_full + PC_NKV;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + PC_NKV);
+  float* sm_f = reinterpret_cast<float*>(tmem_slot + 4);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x, G = gridDim.x;
   const int esz = KV_FP32 ? 4 : 2;
-  const int ppc = PC_ATT_CHUNK_BYTES / (128 * esz);
+  const int ppc = PC_STAGE_BYTES / (128 * esz);             // positions per KV tile
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < PC_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(ptx::smem_u32(b_full + s), 1);
       ptx::mbar_init(ptx::smem_u32(b_empty + s), 1);
     }
@@ -173,14 +204,18 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       ptx::mbar_init(ptx::smem_u32(acc_full + i), 1);
       ptx::mbar_init(ptx::smem_u32(acc_empty + i), 128);
     }
+    for (int i = 0; i < PC_NKV; ++i) {
+      ptx::mbar_init(ptx::smem_u32(kv_full + i), 1);
+      ptx::mbar_init(ptx::smem_u32(kv_empty + i), 1);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), 64);
+    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), Cfg::TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  // zero the B operand once: rows >= R (and the unused hi/lo padding rows) must read as zero forever
-  for (int i = tid; i < PC_B_BYTES / 16; i += PC_THREADS) reinterpret_cast<uint4*>(Bop)[i] = make_uint4(0, 0, 0, 0);
+  // zero the B operand once: rows >= R (hi and lo halves) must read as zero forever
+  for (int i = tid; i < Cfg::B_BYTES / 16; i += PC_THREADS) reinterpret_cast<uint4*>(Bop)[i] = make_uint4(0, 0, 0, 0);
   fence_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
@@ -196,74 +231,67 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     // =================================== PRODUCER ===================================================
     if (lane == 0) {
       const uint64_t pol = ptx::policy_evict_first();
-      uint32_t slot = 0;
-      auto acquire = [&]() -> uint32_t {   // returns stage index; waits until the consumer released it
-        const uint32_t s = slot % PC_STAGES, ph = (slot / PC_STAGES) & 1u;
-        ptx::mbar_wait(ptx::smem_u32(b_empty + s), ph ^ 1u);
-        ++slot;
-        return s;
-      };
+      uint32_t slot = 0, kv_ctr = 0;
       auto gemm_tiles = [&](const CUtensorMap* tmA, const CUtensorMap* tmB2, int split_t, const PcSlice& sl, int layer) {
         for (int i = 0; i < sl.nt; ++i) {
           const int t = sl.t0 + i * sl.G;
           const CUtensorMap* tm = (t < split_t) ? tmA : tmB2;
           const int tt = (t < split_t) ? t : t - split_t;
           for (int kb = sl.kb0; kb < sl.kb1; ++kb) {
-            const uint32_t s = acquire();
+            const uint32_t s = slot % STAGES, ph = (slot / STAGES) & 1u;
+            ++slot;
+            ptx::mbar_wait(ptx::smem_u32(b_empty + s), ph ^ 1u);
             const uint32_t full = ptx::smem_u32(b_full + s);
             ptx::mbar_arrive_expect_tx(full, PC_STAGE_BYTES);
             tma_load_3d(ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES), tm, full, kb * 64, tt * 128, layer, pol);
           }
         }
       };
-      bool waited = false;
+      // KV tiles of this CTA's attention units [from, to) of layer l (positions < pos come from earlier steps)
+      auto kv_units = [&](int l, int from, int to) {
+        const char* kbase = p.kv + (size_t)l * 2 * p.kv_half;
+        const char* vbase = kbase + p.kv_half;
+        int idx = 0;
+        for_each_att_unit(p, cta, G, ppc, [&](int r, int h, int c, int L, int cr) {
+          const int my = idx++;
+          if (my < from || my >= to) return;
+          const int p0 = c * ppc;
+          const int npos = min(L - 1, p0 + ppc) - p0;        // the current position comes from registers
+          if (npos <= 0) return;
+          const uint32_t ks = kv_ctr % PC_NKV, ph = (kv_ctr / PC_NKV) & 1u;
+          ++kv_ctr;
+          ptx::mbar_wait(ptx::smem_u32(kv_empty + ks), ph ^ 1u);
+          const size_t off = (((size_t)cr * p.H + h) * p.S_max + p0) * 128 * esz;
+          const uint32_t bytes = (uint32_t)npos * 128 * esz;
+          const uint32_t full = ptx::smem_u32(kv_full + ks);
+          ptx::mbar_arrive_expect_tx(full, 2 * bytes);
+          uint8_t* dst = kvbuf + (size_t)ks * 2 * PC_STAGE_BYTES;
+          bulk_load(ptx::smem_u32(dst), kbase + off, bytes, full);
+          bulk_load(ptx::smem_u32(dst + PC_STAGE_BYTES), vbase + off, bytes, full);
+        });
+      };
       for (int l = 0; l < p.n_layer; ++l) {
-        gemm_tiles(&tm_qkv, &tm_qkv, 1 << 30, s_qkv, l);
-        // ---- KV tiles of this CTA's attention units (positions < pos are from earlier steps)
-        if (!waited) { pdl_wait(); waited = true; }   // pos[] is written by the previous sampler kernel
-        {
-          const char* kbase = p.kv + (size_t)l * 2 * p.kv_half;
-          const char* vbase = kbase + p.kv_half;
-          int unit0 = 0;
-          for (int r = 0; r < p.R; ++r) {
-            const int u = p.st.slot_map[r >> 1];
-            const int cr = 2 * u + (r & 1);
-            const int L = p.st.pos[u] + 1;
-            const int nch = att_chunks(L, ppc);
-            for (int h = 0; h < p.H; ++h) {
-              // units of (r, h) are unit0 + [0, nch); this CTA takes those == cta (mod G)
-              int first = (cta - (unit0 % G) + G) % G;
-              for (int c = first; c < nch; c += G) {
-                const int p0 = c * ppc;
-                const int pend = min(L - 1, p0 + ppc);        // the current position comes from registers
-                const int npos = pend - p0;
-                if (npos > 0) {
-                  const size_t off = (((size_t)cr * p.H + h) * p.S_max + p0) * 128 * esz;
-                  const uint32_t bytes = (uint32_t)npos * 128 * esz;
-                  uint32_t s = acquire();
-                  uint32_t full = ptx::smem_u32(b_full + s);
-                  ptx::mbar_arrive_expect_tx(full, bytes);
-                  bulk_load(ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES), kbase + off, bytes, full);
-                  s = acquire();
-                  full = ptx::smem_u32(b_full + s);
-                  ptx::mbar_arrive_expect_tx(full, bytes);
-                  bulk_load(ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES), vbase + off, bytes, full);
-                }
-              }
-              unit0 += nch;
-            }
-          }
+        if (l == 0) {
+          gemm_tiles(&tm_qkv, &tm_qkv, 1 << 30, s_qkv, 0);   // weights first: they need nothing from the previous kernel
+          pdl_wait();                                         // pos[] is written by the previous sampler kernel
+          kv_units(0, 0, 1 << 30);
+        } else {
+          kv_units(l, PC_NKV, 1 << 30);                       // (units beyond the prefetched ones)
         }
         gemm_tiles(&tm_o, &tm_o, 1 << 30, s_o, l);
         gemm_tiles(&tm_w1, &tm_w3, T1, s_w13, l);
         gemm_tiles(&tm_w2, &tm_w2, 1 << 30, s_w2, l);
+        if (l + 1 < p.n_layer) {
+          kv_units(l + 1, 0, PC_NKV);                         // next layer's first KV tiles ride ahead of its QKV GEMM
+          gemm_tiles(&tm_qkv, &tm_qkv, 1 << 30, s_qkv, l + 1);
+        }
       }
       gemm_tiles(&tm_head, &tm_head, 1 << 30, s_head, 0);
     }
   } else if (warp == 1) {
     // =================================== MMA ISSUER =================================================
     if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_bf16(128, PC_NB);
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, NB);
       uint32_t slot = 0, tile_ctr = 0, bphase = 0;
       auto gemm_phase = [&](const PcSlice& sl) {
         if (sl.nt == 0) return;
@@ -274,14 +302,14 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           const uint32_t ab = tile_ctr & 1u, aph = (tile_ctr >> 1) & 1u;
           ptx::mbar_wait(ptx::smem_u32(acc_empty + ab), aph ^ 1u);   // epilogue drained this accumulator
           ptx::tc_fence_after();
-          const uint32_t dcol = tmem_base + ab * PC_NB;
+          const uint32_t dcol = tmem_base + ab * NB;
           for (int kb = sl.kb0; kb < sl.kb1; ++kb) {
-            const uint32_t s = slot % PC_STAGES, ph = (slot / PC_STAGES) & 1u;
+            const uint32_t s = slot % STAGES, ph = (slot / STAGES) & 1u;
             ++slot;
             ptx::mbar_wait(ptx::smem_u32(b_full + s), ph);
             ptx::tc_fence_after();
             const uint64_t ad = ptx::umma_desc_k_sw128(ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES));
-            const uint64_t bd = ptx::umma_desc_k_sw128(ptx::smem_u32(Bop + (size_t)(kb - sl.kb0) * (PC_NB * 128)));
+            const uint64_t bd = ptx::umma_desc_k_sw128(ptx::smem_u32(Bop + (size_t)(kb - sl.kb0) * (NB * 128)));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               ptx::umma_bf16(dcol, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb != sl.kb0) || k != 0));
@@ -291,24 +319,8 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           ++tile_ctr;
         }
       };
-      bool waited = false;
       for (int l = 0; l < p.n_layer; ++l) {
         gemm_phase(s_qkv);
-        if (!waited) { pdl_wait(); waited = true; }
-        {  // skip the ring slots the attention units of this CTA consume
-          int unit0 = 0;
-          for (int r = 0; r < p.R; ++r) {
-            const int u = p.st.slot_map[r >> 1];
-            const int L = p.st.pos[u] + 1;
-            const int nch = att_chunks(L, ppc);
-            for (int h = 0; h < p.H; ++h) {
-              int first = (cta - (unit0 % G) + G) % G;
-              for (int c = first; c < nch; c += G)
-                if (min(L - 1, c * ppc + ppc) - c * ppc > 0) slot += 2;
-              unit0 += nch;
-            }
-          }
-        }
         gemm_phase(s_o);
         gemm_phase(s_w13);
         gemm_phase(s_w2);
@@ -324,7 +336,9 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     float* sm_m = sm_f + 1024;          // [8]
     float* sm_l = sm_m + 8;             // [8]
     float* sm_rs = sm_l + 8;            // [PC_RPAD]
-    uint32_t slot = 0, tile_ctr = 0, bar_idx = 0;
+    float* sm_cur = sm_rs + PC_RPAD;    // [2][128] k, v of the current token
+    float* sm_red = sm_cur + 256;       // [PC_RPAD][4] partial sums of squares
+    uint32_t tile_ctr = 0, bar_idx = 0, kv_ctr = 0;
     pdl_wait();                         // state / x inputs of the previous kernels are visible
     int ev = 0;
     auto stamp = [&]() {
@@ -333,10 +347,9 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     };
     stamp();
 
-    auto grid_arrive = [&]() {          // all compute threads have fenced their global writes
-      __threadfence();
+    auto grid_arrive = [&]() {          // bar.sync orders every compute thread's writes before the release
       compute_sync();
-      if (ct == 0) atomicAdd(p.bar, 1u);
+      if (ct == 0) red_release_inc(p.bar);
       ++bar_idx;
     };
     auto grid_wait = [&]() {            // wait for arrival #bar_idx of every CTA
@@ -354,35 +367,67 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       compute_sync();
       if (ct == 0) ptx::mbar_arrive(ptx::smem_u32(b_ready));
     };
-    // RMSNorm statistics of the R rows of x (fast_model.py:254-255): sm_rs[n] = rsqrt(mean(x^2) + eps)
-    auto row_rstd = [&]() {
-      for (int n = cw; n < p.R; n += 4) {
-        const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)n * p.D);
-        float ss = 0.f;
-        for (int i = lane; i < p.D / 4; i += 32) {
-          const float4 v = __ldcg(xr + i);
-          ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
-        }
-        ss = warp_sum(ss);
-        if (lane == 0) sm_rs[n] = rsqrtf(ss / (float)p.D + p.eps);
-      }
-      compute_sync();
-    };
-    // B <- hi/lo split of (x * rstd) * gain over this CTA's K range
+    // B <- hi/lo split of (x * rstd) * gain over this CTA's K range; RMSNorm statistics (fast_model.py:254-255)
+    // and the chunk loads are issued together so the phase costs ONE L2 round trip.
     auto stage_norm = [&](const PcSlice& sl, const __nv_bfloat16* gain) {
       if (sl.nt == 0) return;
-      row_rstd();
       const int nchunk = (sl.kb1 - sl.kb0) * 8;
-      for (int i = ct; i < p.R * nchunk; i += 128) {
+      const int total = p.R * nchunk;
+      constexpr int MAXC = 3;             // chunks pre-loaded per thread (covers R = 2 completely)
+      float4 ca[MAXC], cb[MAXC];
+#pragma unroll
+      for (int j = 0; j < MAXC; ++j) {
+        const int i = ct + j * 128;
+        if (i < total) {
+          const int n = i / nchunk, c = i - n * nchunk;
+          const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)n * p.D + sl.kb0 * 64 + c * 8);
+          ca[j] = __ldcg(xr);
+          cb[j] = __ldcg(xr + 1);
+        }
+      }
+      const int f4_per_row = p.D >> 2;
+      for (int n0 = 0; n0 < p.R; n0 += 4) {
+        float ss[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int n = n0 + q;
+          if (n < p.R) {
+            const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)n * p.D);
+            for (int i = ct; i < f4_per_row; i += 128) {
+              const float4 v = __ldcg(xr + i);
+              ss[q] = fmaf(v.x, v.x, ss[q]); ss[q] = fmaf(v.y, v.y, ss[q]);
+              ss[q] = fmaf(v.z, v.z, ss[q]); ss[q] = fmaf(v.w, v.w, ss[q]);
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float s = warp_sum(ss[q]);
+          if (lane == 0 && n0 + q < p.R) sm_red[(n0 + q) * 4 + cw] = s;
+        }
+      }
+      compute_sync();
+      if (ct < p.R) {
+        const float t = sm_red[ct * 4] + sm_red[ct * 4 + 1] + sm_red[ct * 4 + 2] + sm_red[ct * 4 + 3];
+        sm_rs[ct] = rsqrtf(t / (float)p.D + p.eps);
+      }
+      compute_sync();
+      auto emit = [&](int i, const float4& a, const float4& b) {
         const int n = i / nchunk, c = i - n * nchunk;
         const int k = sl.kb0 * 64 + c * 8;
-        const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)n * p.D + k);
-        const float4 a = __ldcg(xr), b = __ldcg(xr + 1);
         const uint4 gw = *reinterpret_cast<const uint4*>(gain + k);
         const float rs = sm_rs[n];
         float v[8] = {(a.x * rs) * bf_lo(gw.x), (a.y * rs) * bf_hi(gw.x), (a.z * rs) * bf_lo(gw.y), (a.w * rs) * bf_hi(gw.y),
                       (b.x * rs) * bf_lo(gw.z), (b.y * rs) * bf_hi(gw.z), (b.z * rs) * bf_lo(gw.w), (b.w * rs) * bf_hi(gw.w)};
-        b_store8(Bop, c >> 3, n, c & 7, v);
+        b_store8<NB>(Bop, c >> 3, n, c & 7, v);
+      };
+#pragma unroll
+      for (int j = 0; j < MAXC; ++j)
+        if (ct + j * 128 < total) emit(ct + j * 128, ca[j], cb[j]);
+      for (int i = ct + MAXC * 128; i < total; i += 128) {
+        const int n = i / nchunk, c = i - n * nchunk;
+        const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)n * p.D + sl.kb0 * 64 + c * 8);
+        emit(i, __ldcg(xr), __ldcg(xr + 1));
       }
       b_publish();
     };
@@ -394,10 +439,14 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         ++tile_ctr;
         ptx::mbar_wait(ptx::smem_u32(acc_full + ab), aph);
         ptx::tc_fence_after();
-        uint32_t hi[16], lo[16];
-        const uint32_t ta = tmem_base + ((uint32_t)(32 * quad) << 16) + ab * PC_NB;
-        ptx::tmem_ld16(ta, hi);
-        ptx::tmem_ld16(ta + PC_RPAD, lo);
+        uint32_t acc[NB];
+        const uint32_t ta = tmem_base + ((uint32_t)(32 * quad) << 16) + ab * NB;
+        if (NB == 16) {
+          ptx::tmem_ld16(ta, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
+        } else {
+          ptx::tmem_ld16(ta, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
+          ptx::tmem_ld16(ta + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[NB - 16]));
+        }
         ptx::tmem_ld_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(ptx::smem_u32(acc_empty + ab));
@@ -405,8 +454,8 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         const int j = ((t < split_t) ? t : t - split_t) * 128 + 32 * quad + lane;
         if (j < M) {
 #pragma unroll
-          for (int n = 0; n < PC_RPAD; ++n)
-            if (n < p.R) atomicAdd(o + (size_t)n * ldo + j, __uint_as_float(hi[n]) + __uint_as_float(lo[n]));
+          for (int n = 0; n < RH; ++n)
+            if (n < p.R) atomicAdd(o + (size_t)n * ldo + j, __uint_as_float(acc[n]) + __uint_as_float(acc[RH + n]));
         }
       }
     };
@@ -438,7 +487,6 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       stage_norm(s_qkv, p.attn_norm + lo_);
       stamp();
       epilogue(s_qkv, p.qkv, 3 * p.D, 3 * p.D, 1 << 30, nullptr);
-      slot += (uint32_t)(s_qkv.nt * (s_qkv.kb1 - s_qkv.kb0));
       stamp();
       grid_arrive();
 
@@ -450,129 +498,112 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         char* kbase = p.kv + (size_t)l * 2 * p.kv_half;
         char* vbase = kbase + p.kv_half;
         const int half = lane >> 4, sub = lane & 15;
-        int unit0 = 0;
-        for (int r = 0; r < p.R; ++r) {
-          const int u = p.st.slot_map[r >> 1];
-          const int cr = 2 * u + (r & 1);
-          const int L = p.st.pos[u] + 1;
-          const int nch = att_chunks(L, ppc);
-          for (int h = 0; h < p.H; ++h) {
-            int first = (cta - (unit0 % G) + G) % G;
-            for (int c = first; c < nch; c += G) {
-              const int p0 = c * ppc;
-              const int pend = min(L - 1, p0 + ppc);
-              const int npos = pend - p0;
-              const bool has_cur = (p0 + ppc >= L);   // this chunk owns the current position L-1
-              const float* qrow = p.qkv + (size_t)r * 3 * p.D + h * 128;
-              float q[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) q[i] = __ldcg(qrow + sub * 8 + i) * 0.08838834764831845f;
-              float m = -INFINITY, lsum = 0.f, o[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = 0.f;
-              if (npos > 0) {
-                const uint32_t sk = slot % PC_STAGES, phk = (slot / PC_STAGES) & 1u;
-                const uint32_t sv = (slot + 1) % PC_STAGES, phv = ((slot + 1) / PC_STAGES) & 1u;
-                slot += 2;
-                ptx::mbar_wait(ptx::smem_u32(b_full + sk), phk);
-                ptx::mbar_wait(ptx::smem_u32(b_full + sv), phv);
-                const uint8_t* kt = ring + (size_t)sk * PC_STAGE_BYTES;
-                const uint8_t* vt = ring + (size_t)sv * PC_STAGE_BYTES;
-                for (int pb = cw * 2; pb < npos; pb += 8) {
-                  const int pp = pb + half;
-                  const bool valid = pp < npos;
-                  float kv[8], s = 0.f;
-                  if (valid) {
-                    load8s<KV_FP32>(kt, pp, sub, kv);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) s = fmaf(q[i], kv[i], s);
-                  }
-                  s += __shfl_xor_sync(0xffffffffu, s, 8);
-                  s += __shfl_xor_sync(0xffffffffu, s, 4);
-                  s += __shfl_xor_sync(0xffffffffu, s, 2);
-                  s += __shfl_xor_sync(0xffffffffu, s, 1);
-                  if (valid) {
-                    load8s<KV_FP32>(vt, pp, sub, kv);
-                    const float mn = fmaxf(m, s), corr = __expf(m - mn), pw = __expf(s - mn);
-                    lsum = lsum * corr + pw;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + pw * kv[i];
-                    m = mn;
-                  }
-                }
-                compute_sync();   // every warp is done with both tiles
-                if (ct == 0) {
-                  ptx::mbar_arrive(ptx::smem_u32(b_empty + sk));
-                  ptx::mbar_arrive(ptx::smem_u32(b_empty + sv));
-                }
-              }
-              if (has_cur) {
-                // the new token's k, v: complete sums from the qkv buffer, rounded like the cache stores them,
-                // appended to the cache and attended to by half-warp 0 of compute warp 0
-                const float* kc = p.qkv + (size_t)r * 3 * p.D + p.D + h * 128;
-                const float* vc = kc + p.D;
-                const float kval = __ldcg(kc + ct), vval = __ldcg(vc + ct);
-                const size_t e = (((size_t)cr * p.H + h) * p.S_max + (L - 1)) * 128 + ct;
-                if (KV_FP32) {
-                  reinterpret_cast<float*>(kbase)[e] = kval;
-                  reinterpret_cast<float*>(vbase)[e] = vval;
-                } else {
-                  reinterpret_cast<__nv_bfloat16*>(kbase)[e] = __float2bfloat16_rn(kval);
-                  reinterpret_cast<__nv_bfloat16*>(vbase)[e] = __float2bfloat16_rn(vval);
-                }
-                if (cw == 0) {
-                  float kv[8], s = 0.f;
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    const float kk = __ldcg(kc + sub * 8 + i);
-                    kv[i] = KV_FP32 ? kk : __bfloat162float(__float2bfloat16_rn(kk));
-                    s = fmaf(q[i], kv[i], s);
-                  }
-                  s += __shfl_xor_sync(0xffffffffu, s, 8);
-                  s += __shfl_xor_sync(0xffffffffu, s, 4);
-                  s += __shfl_xor_sync(0xffffffffu, s, 2);
-                  s += __shfl_xor_sync(0xffffffffu, s, 1);
-                  if (half == 0) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                      const float vv = __ldcg(vc + sub * 8 + i);
-                      kv[i] = KV_FP32 ? vv : __bfloat162float(__float2bfloat16_rn(vv));
-                    }
-                    const float mn = fmaxf(m, s), corr = __expf(m - mn), pw = __expf(s - mn);
-                    lsum = lsum * corr + pw;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + pw * kv[i];
-                    m = mn;
-                  }
-                }
-              }
-              // merge the 8 half-warp states -> one partial (m, l, o[128]) for this chunk
-              const int gidx = cw * 2 + half;
-              if (sub == 0) { sm_m[gidx] = m; sm_l[gidx] = lsum; }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) sm_o[gidx * 128 + sub * 8 + i] = o[i];
-              compute_sync();
-              {
-                float M = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) M = fmaxf(M, sm_m[i]);
-                float Ls = 0.f, O = 0.f;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  if (sm_m[i] > -INFINITY) {
-                    const float w = __expf(sm_m[i] - M);
-                    Ls += sm_l[i] * w;
-                    O += sm_o[i * 128 + ct] * w;
-                  }
-                const size_t pidx = ((size_t)r * p.H + h) * PC_MAX_CHUNKS + c;
-                p.part_o[pidx * 128 + ct] = O;
-                if (ct == 0) { p.part_ml[pidx * 2] = M; p.part_ml[pidx * 2 + 1] = Ls; }
-              }
-              compute_sync();   // sm_o / sm_m are reused by the next unit
-            }
-            unit0 += nch;
+        const int hw = cw * 2 + half;               // half-warp id 0..7
+        const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
+        for_each_att_unit(p, cta, G, ppc, [&](int r, int h, int c, int L, int cr) {
+          const int p0 = c * ppc;
+          const int npos = min(L - 1, p0 + ppc) - p0;
+          const bool has_cur = (p0 + ppc >= L);     // this chunk owns the current position L-1
+          // one round trip for everything this unit needs from global memory
+          const float* qrow = p.qkv + (size_t)r * 3 * p.D + h * 128;
+          const float4 qa = __ldcg(reinterpret_cast<const float4*>(qrow + sub * 8));
+          const float4 qb = __ldcg(reinterpret_cast<const float4*>(qrow + sub * 8) + 1);
+          float kcur = 0.f, vcur = 0.f;
+          if (has_cur) {
+            kcur = __ldcg(qrow + p.D + ct);
+            vcur = __ldcg(qrow + 2 * p.D + ct);
           }
-        }
+          const float sc = 0.08838834764831845f;   // 1/sqrt(128)
+          const float q[8] = {qa.x * sc, qa.y * sc, qa.z * sc, qa.w * sc, qb.x * sc, qb.y * sc, qb.z * sc, qb.w * sc};
+          float m = -INFINITY, lsum = 0.f, o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = 0.f;
+          if (has_cur) {
+            // append the new token's k, v to the cache, rounded as the cache stores them, and share them via smem
+            const size_t e = (((size_t)cr * p.H + h) * p.S_max + (L - 1)) * 128 + ct;
+            if (KV_FP32) {
+              reinterpret_cast<float*>(kbase)[e] = kcur;
+              reinterpret_cast<float*>(vbase)[e] = vcur;
+            } else {
+              const __nv_bfloat16 kb16 = __float2bfloat16_rn(kcur), vb16 = __float2bfloat16_rn(vcur);
+              reinterpret_cast<__nv_bfloat16*>(kbase)[e] = kb16;
+              reinterpret_cast<__nv_bfloat16*>(vbase)[e] = vb16;
+              kcur = __bfloat162float(kb16);
+              vcur = __bfloat162float(vb16);
+            }
+            sm_cur[ct] = kcur;
+            sm_cur[128 + ct] = vcur;
+          }
+          if (npos > 0) {
+            const uint32_t ks = kv_ctr % PC_NKV, ph = (kv_ctr / PC_NKV) & 1u;
+            ++kv_ctr;
+            ptx::mbar_wait(ptx::smem_u32(kv_full + ks), ph);
+            const uint8_t* kt = kvbuf + (size_t)ks * 2 * PC_STAGE_BYTES;
+            const uint8_t* vt = kt + PC_STAGE_BYTES;
+            // each half-warp owns positions hw, hw+8, ...; two positions per trip for ILP
+            for (int pb = hw; pb < npos; pb += 16) {
+              const int pA = pb, pB = pb + 8;
+              const bool vB = pB < npos;
+              float ka[8], kb2[8], sA = 0.f, sB = 0.f;
+              load8s<KV_FP32>(kt, pA, sub, ka);
+              if (vB) load8s<KV_FP32>(kt, pB, sub, kb2);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                sA = fmaf(q[i], ka[i], sA);
+                if (vB) sB = fmaf(q[i], kb2[i], sB);
+              }
+#pragma unroll
+              for (int off = 8; off > 0; off >>= 1) {   // reduce inside the 16-lane group only: trip counts differ per half-warp
+                sA += __shfl_xor_sync(hmask, sA, off);
+                sB += __shfl_xor_sync(hmask, sB, off);
+              }
+              load8s<KV_FP32>(vt, pA, sub, ka);
+              if (vB) load8s<KV_FP32>(vt, pB, sub, kb2);
+              const float mn = fmaxf(m, vB ? fmaxf(sA, sB) : sA);
+              const float corr = __expf(m - mn), wA = __expf(sA - mn), wB = vB ? __expf(sB - mn) : 0.f;
+              lsum = lsum * corr + wA + wB;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + wA * ka[i] + (vB ? wB * kb2[i] : 0.f);
+              m = mn;
+            }
+          }
+          compute_sync();   // KV tiles fully consumed; sm_cur visible
+          if (npos > 0 && ct == 0) ptx::mbar_arrive(ptx::smem_u32(kv_empty + ((kv_ctr - 1) % PC_NKV)));
+          if (has_cur && hw == 0) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s = fmaf(q[i], sm_cur[sub * 8 + i], s);
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0x0000ffffu, s, off);
+            const float mn = fmaxf(m, s), corr = __expf(m - mn), pw = __expf(s - mn);
+            lsum = lsum * corr + pw;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + pw * sm_cur[128 + sub * 8 + i];
+            m = mn;
+          }
+          // merge the 8 half-warp states -> one partial (m, l, o[128]) for this chunk
+          if (sub == 0) { sm_m[hw] = m; sm_l[hw] = lsum; }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sm_o[hw * 128 + sub * 8 + i] = o[i];
+          compute_sync();
+          {
+            float M = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) M = fmaxf(M, sm_m[i]);
+            float Ls = 0.f, O = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (sm_m[i] > -INFINITY) {
+                const float w = __expf(sm_m[i] - M);
+                Ls += sm_l[i] * w;
+                O += sm_o[i * 128 + ct] * w;
+              }
+            const size_t pidx = ((size_t)r * p.H + h) * PC_MAX_CHUNKS + c;
+            p.part_o[pidx * 128 + ct] = O;
+            if (ct == 0) { p.part_ml[pidx * 2] = M; p.part_ml[pidx * 2 + 1] = Ls; }
+          }
+          compute_sync();   // sm_o / sm_m / sm_cur are reused by the next unit
+        });
       }
       stamp();
       grid_arrive();
@@ -606,13 +637,12 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           const float inv = 1.f / den;
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] *= inv;
-          b_store8(Bop, c >> 3, n, c & 7, v);
+          b_store8<NB>(Bop, c >> 3, n, c & 7, v);
         }
         b_publish();
       }
       stamp();
       epilogue(s_o, p.x, p.D, p.D, 1 << 30, nullptr);
-      slot += (uint32_t)(s_o.nt * (s_o.kb1 - s_o.kb0));
       stamp();
       grid_arrive();
 
@@ -622,7 +652,6 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       stage_norm(s_w13, p.ffn_norm + lo_);
       stamp();
       epilogue(s_w13, p.gu, 2 * p.F, p.F, T1, p.gu + p.F);
-      slot += (uint32_t)(s_w13.nt * (s_w13.kb1 - s_w13.kb0));
       stamp();
       grid_arrive();
 
@@ -642,13 +671,12 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           float v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = (g[e] / (1.f + expf(-g[e]))) * uu[e];
-          b_store8(Bop, c >> 3, n, c & 7, v);
+          b_store8<NB>(Bop, c >> 3, n, c & 7, v);
         }
         b_publish();
       }
       stamp();
       epilogue(s_w2, p.x, p.D, p.D, 1 << 30, nullptr);
-      slot += (uint32_t)(s_w2.nt * (s_w2.kb1 - s_w2.kb0));
       stamp();
       grid_arrive();
     }
@@ -665,7 +693,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 64);
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

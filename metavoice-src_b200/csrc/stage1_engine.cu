@@ -522,21 +522,24 @@ static int launch_persistent(mvb_s1* h, cudaStream_t s, int n_utts) {
   p.bar = h->wsp<unsigned>(h->L.c_bar);
   p.trace = (h->trace && h->n_sm <= 160) ? h->wsp<long long>(h->L.c_trace) : nullptr;
   p.st = h->st;
-  const size_t smem = 1024 + (size_t)PC_STAGES * PC_STAGE_BYTES + PC_B_BYTES + 25 * 8 + 16 + (1024 + 8 + 8 + PC_RPAD) * 4 + 64;
-  static bool attr_set[2] = {false, false};
-  const int fp = p.kv_fp32 ? 1 : 0;
-  if (!attr_set[fp]) {
-    if (fp) CK(cudaFuncSetAttribute(k_decode_persistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else CK(cudaFuncSetAttribute(k_decode_persistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[fp] = true;
-  }
   h->launches++;
-  if (fp)
-    CK(launch_pdl(h->pdl, k_decode_persistent<true>, dim3(h->n_sm), dim3(PC_THREADS), smem, s, h->tm3[0], h->tm3[1], h->tm3[2],
-                  h->tm3[3], h->tm3[4], h->tm3[5], p));
-  else
-    CK(launch_pdl(h->pdl, k_decode_persistent<false>, dim3(h->n_sm), dim3(PC_THREADS), smem, s, h->tm3[0], h->tm3[1], h->tm3[2],
-                  h->tm3[3], h->tm3[4], h->tm3[5], p));
+  const bool fp = p.kv_fp32 != 0, wide = p.R > PcCfg<16>::RH;
+#define MVB_PC_LAUNCH(FP, NBV, IDX)                                                                                   \
+  do {                                                                                                                \
+    static bool attr_set = false;                                                                                     \
+    if (!attr_set) {                                                                                                  \
+      CK(cudaFuncSetAttribute(k_decode_persistent<FP, NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                              (int)PcCfg<NBV>::SMEM));                                                                \
+      attr_set = true;                                                                                                \
+    }                                                                                                                 \
+    CK(launch_pdl(h->pdl, k_decode_persistent<FP, NBV>, dim3(h->n_sm), dim3(PC_THREADS), PcCfg<NBV>::SMEM, s,         \
+                  h->tm3[0], h->tm3[1], h->tm3[2], h->tm3[3], h->tm3[4], h->tm3[5], p));                              \
+  } while (0)
+  if (fp && wide) MVB_PC_LAUNCH(true, 32, 0);
+  else if (fp) MVB_PC_LAUNCH(true, 16, 1);
+  else if (wide) MVB_PC_LAUNCH(false, 32, 2);
+  else MVB_PC_LAUNCH(false, 16, 3);
+#undef MVB_PC_LAUNCH
   return MVB_OK;
 }
 

@@ -107,7 +107,7 @@ def generate(model: Transformer, prompt: torch.Tensor, spk_emb: torch.Tensor, *,
 @torch.no_grad()
 def generate_batch(model: Transformer, prompts, spk_embs: torch.Tensor, *, max_new_tokens: Optional[int] = None,
                    end_of_audio_token: int = 2048, noise=None, forced=None, seed: Optional[int] = None,
-                   guidance_scale=3.0, temperature=1.0, top_p=None, top_k=None):
+                   guidance_scale=3.0, temperature=1.0, top_p=None, top_k=None, return_sampled: bool = False):
     """N independent utterances decoded together with per-utterance positions (the batching semantics of
     fam/llm/mixins/causal.py:179-287, numerically equal to running each utterance alone).  Goes through the
     HOST-buffer plugin call ``mvb_s1_generate``: prompts/speakers are copied host->device and the tokens
@@ -142,7 +142,16 @@ def generate_batch(model: Transformer, prompts, spk_embs: torch.Tensor, *, max_n
     vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
     _lib.check(model._lib.mvb_s1_generate(model.handle, n, vp(flat), vp(lens), vp(spk), params, max_new, vp(nz), vp(fc),
                                           vp(out), vp(out_lens), model._stream()))
-    return [torch.from_numpy(out[i, :out_lens[i]].copy()) for i in range(n)]
+    fed = [torch.from_numpy(out[i, :out_lens[i]].copy()) for i in range(n)]
+    if not return_sampled:
+        return fed
+    # test hook: the sampler's own draws (they differ from the fed-back tokens only under teacher forcing)
+    sampled = []
+    for i in range(n):
+        buf = np.zeros(int(out_lens[i]), dtype=np.int32)
+        _lib.check(model._lib.mvb_s1_fetch_sampled(model.handle, i, vp(buf), int(out_lens[i]), model._stream()))
+        sampled.append(torch.from_numpy(buf))
+    return fed, sampled
 
 
 def encode_tokens(tokenizer, text: str, device="cuda") -> torch.Tensor:
