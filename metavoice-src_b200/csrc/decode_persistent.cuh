@@ -129,24 +129,41 @@ __device__ __forceinline__ PcSlice pc_slice(const PcMat& m, int cta) {
   return s;
 }
 
-__device__ __forceinline__ int att_chunks(int L, int ppc) { return (L + ppc - 1) / ppc; }
-
-// Enumerates this CTA's attention units of one layer in a fixed order: unit = (row r, head h, chunk c), global
-// unit ids are dealt round-robin to CTAs.  Producer and compute warps walk the identical sequence.
-struct AttIter {
-  int r, h, c, unit0, L, nch, cr;
+// Attention work decomposition of one layer.  A unit = (activation row r, head h, split z): a contiguous run of
+// KV tiles (ppc positions each) of that row's cache; every (r, h) is cut into nz <= zmax splits so that about one
+// unit lands on every CTA at batch 1 while large batches get one multi-tile unit per (r, h).  Global unit ids are
+// dealt round-robin to CTAs; the producer and the compute warps walk the identical sequence.
+struct AttSplit {
+  int tt, tps, nz;   // tiles of the row, tiles per split, number of splits
 };
-template <typename F>
-__device__ __forceinline__ void for_each_att_unit(const PcParams& p, int cta, int G, int ppc, F&& f) {
+__device__ __forceinline__ AttSplit att_split(int L, int ppc, int zmax) {
+  AttSplit a;
+  a.tt = (L + ppc - 1) / ppc;
+  const int zr = min(zmax, a.tt);
+  a.tps = (a.tt + zr - 1) / zr;
+  a.nz = (a.tt + a.tps - 1) / a.tps;
+  return a;
+}
+template <typename FU, typename FT, typename FE>
+__device__ __forceinline__ void for_each_att(const PcParams& p, int cta, int G, int ppc, FU&& unit_begin, FT&& tile, FE&& unit_end) {
+  const int zmax = max(1, G / (p.R * p.H));
   int unit0 = 0;
   for (int r = 0; r < p.R; ++r) {
     const int u = p.st.slot_map[r >> 1];
     const int L = p.st.pos[u] + 1;
-    const int nch = att_chunks(L, ppc);
+    const AttSplit a = att_split(L, ppc, zmax);
     for (int h = 0; h < p.H; ++h) {
       const int first = (cta - (unit0 % G) + G) % G;
-      for (int c = first; c < nch; c += G) f(r, h, c, L, 2 * u + (r & 1));
-      unit0 += nch;
+      for (int z = first; z < a.nz; z += G) {
+        const int t1 = min(a.tt, (z + 1) * a.tps);
+        unit_begin(r, h, z, L, 2 * u + (r & 1), t1 == a.tt);
+        for (int t = z * a.tps; t < t1; ++t) {
+          const int p0 = t * ppc;
+          tile(r, h, p0, min(L - 1, p0 + ppc) - p0, p0 + ppc >= L, L, 2 * u + (r & 1));
+        }
+        unit_end(r, h, z);
+      }
+      unit0 += a.nz;
     }
   }
 }
@@ -247,28 +264,28 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           }
         }
       };
-      // KV tiles of this CTA's attention units [from, to) of layer l (positions < pos come from earlier steps)
+      // KV tiles [from, to) (in this CTA's tile order) of layer l; positions < pos come from earlier steps
       auto kv_units = [&](int l, int from, int to) {
         const char* kbase = p.kv + (size_t)l * 2 * p.kv_half;
         const char* vbase = kbase + p.kv_half;
         int idx = 0;
-        for_each_att_unit(p, cta, G, ppc, [&](int r, int h, int c, int L, int cr) {
-          const int my = idx++;
-          if (my < from || my >= to) return;
-          const int p0 = c * ppc;
-          const int npos = min(L - 1, p0 + ppc) - p0;        // the current position comes from registers
-          if (npos <= 0) return;
-          const uint32_t ks = kv_ctr % PC_NKV, ph = (kv_ctr / PC_NKV) & 1u;
-          ++kv_ctr;
-          ptx::mbar_wait(ptx::smem_u32(kv_empty + ks), ph ^ 1u);
-          const size_t off = (((size_t)cr * p.H + h) * p.S_max + p0) * 128 * esz;
-          const uint32_t bytes = (uint32_t)npos * 128 * esz;
-          const uint32_t full = ptx::smem_u32(kv_full + ks);
-          ptx::mbar_arrive_expect_tx(full, 2 * bytes);
-          uint8_t* dst = kvbuf + (size_t)ks * 2 * PC_STAGE_BYTES;
-          bulk_load(ptx::smem_u32(dst), kbase + off, bytes, full);
-          bulk_load(ptx::smem_u32(dst + PC_STAGE_BYTES), vbase + off, bytes, full);
-        });
+        for_each_att(p, cta, G, ppc, [&](int, int, int, int, int, bool) {},
+                     [&](int r, int h, int p0, int npos, bool, int, int cr) {
+                       if (npos <= 0) return;               // only the current position: it comes from registers
+                       const int my = idx++;
+                       if (my < from || my >= to) return;
+                       const uint32_t ks = kv_ctr % PC_NKV, ph = (kv_ctr / PC_NKV) & 1u;
+                       ++kv_ctr;
+                       ptx::mbar_wait(ptx::smem_u32(kv_empty + ks), ph ^ 1u);
+                       const size_t off = (((size_t)cr * p.H + h) * p.S_max + p0) * 128 * esz;
+                       const uint32_t bytes = (uint32_t)npos * 128 * esz;
+                       const uint32_t full = ptx::smem_u32(kv_full + ks);
+                       ptx::mbar_arrive_expect_tx(full, 2 * bytes);
+                       uint8_t* dst = kvbuf + (size_t)ks * 2 * PC_STAGE_BYTES;
+                       bulk_load(ptx::smem_u32(dst), kbase + off, bytes, full);
+                       bulk_load(ptx::smem_u32(dst + PC_STAGE_BYTES), vbase + off, bytes, full);
+                     },
+                     [&](int, int, int) {});
       };
       for (int l = 0; l < p.n_layer; ++l) {
         if (l == 0) {
@@ -491,119 +508,123 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       grid_arrive();
 
       // ---- attention over [0, pos] + KV-cache append (fast_model.py:104-113, 220-224)
+      zero_slice(p.gu, (size_t)PC_RPAD * 2 * p.F);   // free since the previous layer's w2 phase; ordered by the next arrive
       grid_wait();
       stamp();
-      zero_slice(p.gu, (size_t)PC_RPAD * 2 * p.F);
       {
         char* kbase = p.kv + (size_t)l * 2 * p.kv_half;
         char* vbase = kbase + p.kv_half;
         const int half = lane >> 4, sub = lane & 15;
         const int hw = cw * 2 + half;               // half-warp id 0..7
         const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
-        for_each_att_unit(p, cta, G, ppc, [&](int r, int h, int c, int L, int cr) {
-          const int p0 = c * ppc;
-          const int npos = min(L - 1, p0 + ppc) - p0;
-          const bool has_cur = (p0 + ppc >= L);     // this chunk owns the current position L-1
-          // one round trip for everything this unit needs from global memory
-          const float* qrow = p.qkv + (size_t)r * 3 * p.D + h * 128;
-          const float4 qa = __ldcg(reinterpret_cast<const float4*>(qrow + sub * 8));
-          const float4 qb = __ldcg(reinterpret_cast<const float4*>(qrow + sub * 8) + 1);
-          float kcur = 0.f, vcur = 0.f;
-          if (has_cur) {
-            kcur = __ldcg(qrow + p.D + ct);
-            vcur = __ldcg(qrow + 2 * p.D + ct);
-          }
-          const float sc = 0.08838834764831845f;   // 1/sqrt(128)
-          const float q[8] = {qa.x * sc, qa.y * sc, qa.z * sc, qa.w * sc, qb.x * sc, qb.y * sc, qb.z * sc, qb.w * sc};
-          float m = -INFINITY, lsum = 0.f, o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = 0.f;
-          if (has_cur) {
-            // append the new token's k, v to the cache, rounded as the cache stores them, and share them via smem
-            const size_t e = (((size_t)cr * p.H + h) * p.S_max + (L - 1)) * 128 + ct;
-            if (KV_FP32) {
-              reinterpret_cast<float*>(kbase)[e] = kcur;
-              reinterpret_cast<float*>(vbase)[e] = vcur;
-            } else {
-              const __nv_bfloat16 kb16 = __float2bfloat16_rn(kcur), vb16 = __float2bfloat16_rn(vcur);
-              reinterpret_cast<__nv_bfloat16*>(kbase)[e] = kb16;
-              reinterpret_cast<__nv_bfloat16*>(vbase)[e] = vb16;
-              kcur = __bfloat162float(kb16);
-              vcur = __bfloat162float(vb16);
+        float q[8], o[8], m = -INFINITY, lsum = 0.f, kcur = 0.f, vcur = 0.f;
+        for_each_att(p, cta, G, ppc,
+          // ---- unit begin: one round trip for everything the unit needs from global memory
+          [&](int r, int h, int z, int L, int cr, bool owns_cur) {
+            const float* qrow = p.qkv + (size_t)r * 3 * p.D + h * 128;
+            const float4 qa = __ldcg(reinterpret_cast<const float4*>(qrow + sub * 8));
+            const float4 qb = __ldcg(reinterpret_cast<const float4*>(qrow + sub * 8) + 1);
+            if (owns_cur) {
+              kcur = __ldcg(qrow + p.D + ct);
+              vcur = __ldcg(qrow + 2 * p.D + ct);
             }
-            sm_cur[ct] = kcur;
-            sm_cur[128 + ct] = vcur;
-          }
-          if (npos > 0) {
-            const uint32_t ks = kv_ctr % PC_NKV, ph = (kv_ctr / PC_NKV) & 1u;
-            ++kv_ctr;
-            ptx::mbar_wait(ptx::smem_u32(kv_full + ks), ph);
-            const uint8_t* kt = kvbuf + (size_t)ks * 2 * PC_STAGE_BYTES;
-            const uint8_t* vt = kt + PC_STAGE_BYTES;
-            // each half-warp owns positions hw, hw+8, ...; two positions per trip for ILP
-            for (int pb = hw; pb < npos; pb += 16) {
-              const int pA = pb, pB = pb + 8;
-              const bool vB = pB < npos;
-              float ka[8], kb2[8], sA = 0.f, sB = 0.f;
-              load8s<KV_FP32>(kt, pA, sub, ka);
-              if (vB) load8s<KV_FP32>(kt, pB, sub, kb2);
+            const float sc = 0.08838834764831845f;   // 1/sqrt(128)
+            q[0] = qa.x * sc; q[1] = qa.y * sc; q[2] = qa.z * sc; q[3] = qa.w * sc;
+            q[4] = qb.x * sc; q[5] = qb.y * sc; q[6] = qb.z * sc; q[7] = qb.w * sc;
+            m = -INFINITY; lsum = 0.f;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                sA = fmaf(q[i], ka[i], sA);
-                if (vB) sB = fmaf(q[i], kb2[i], sB);
+            for (int i = 0; i < 8; ++i) o[i] = 0.f;
+          },
+          // ---- one KV tile (and, on the row's last tile, the current token)
+          [&](int r, int h, int p0, int npos, bool has_cur, int L, int cr) {
+            if (has_cur) {
+              // append the new token's k, v to the cache, rounded as the cache stores them; share them via smem
+              const size_t e = (((size_t)cr * p.H + h) * p.S_max + (L - 1)) * 128 + ct;
+              if (KV_FP32) {
+                reinterpret_cast<float*>(kbase)[e] = kcur;
+                reinterpret_cast<float*>(vbase)[e] = vcur;
+              } else {
+                const __nv_bfloat16 kb16 = __float2bfloat16_rn(kcur), vb16 = __float2bfloat16_rn(vcur);
+                reinterpret_cast<__nv_bfloat16*>(kbase)[e] = kb16;
+                reinterpret_cast<__nv_bfloat16*>(vbase)[e] = vb16;
+                kcur = __bfloat162float(kb16);
+                vcur = __bfloat162float(vb16);
               }
+              sm_cur[ct] = kcur;
+              sm_cur[128 + ct] = vcur;
+            }
+            if (npos > 0) {
+              const uint32_t ks = kv_ctr % PC_NKV, ph = (kv_ctr / PC_NKV) & 1u;
+              ++kv_ctr;
+              ptx::mbar_wait(ptx::smem_u32(kv_full + ks), ph);
+              const uint8_t* kt = kvbuf + (size_t)ks * 2 * PC_STAGE_BYTES;
+              const uint8_t* vt = kt + PC_STAGE_BYTES;
+              // each half-warp owns positions hw, hw+8, ...; two positions per trip for ILP
+              for (int pb = hw; pb < npos; pb += 16) {
+                const int pA = pb, pB = pb + 8;
+                const bool vB = pB < npos;
+                float ka[8], kb2[8], sA = 0.f, sB = 0.f;
+                load8s<KV_FP32>(kt, pA, sub, ka);
+                if (vB) load8s<KV_FP32>(kt, pB, sub, kb2);
 #pragma unroll
-              for (int off = 8; off > 0; off >>= 1) {   // reduce inside the 16-lane group only: trip counts differ per half-warp
-                sA += __shfl_xor_sync(hmask, sA, off);
-                sB += __shfl_xor_sync(hmask, sB, off);
+                for (int i = 0; i < 8; ++i) {
+                  sA = fmaf(q[i], ka[i], sA);
+                  if (vB) sB = fmaf(q[i], kb2[i], sB);
+                }
+#pragma unroll
+                for (int off = 8; off > 0; off >>= 1) {   // reduce inside the 16-lane group only: trip counts differ per half-warp
+                  sA += __shfl_xor_sync(hmask, sA, off);
+                  sB += __shfl_xor_sync(hmask, sB, off);
+                }
+                load8s<KV_FP32>(vt, pA, sub, ka);
+                if (vB) load8s<KV_FP32>(vt, pB, sub, kb2);
+                const float mn = fmaxf(m, vB ? fmaxf(sA, sB) : sA);
+                const float corr = __expf(m - mn), wA = __expf(sA - mn), wB = vB ? __expf(sB - mn) : 0.f;
+                lsum = lsum * corr + wA + wB;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + wA * ka[i] + (vB ? wB * kb2[i] : 0.f);
+                m = mn;
               }
-              load8s<KV_FP32>(vt, pA, sub, ka);
-              if (vB) load8s<KV_FP32>(vt, pB, sub, kb2);
-              const float mn = fmaxf(m, vB ? fmaxf(sA, sB) : sA);
-              const float corr = __expf(m - mn), wA = __expf(sA - mn), wB = vB ? __expf(sB - mn) : 0.f;
-              lsum = lsum * corr + wA + wB;
+            }
+            if (npos > 0 || has_cur) compute_sync();   // KV tile fully consumed; sm_cur visible
+            if (npos > 0 && ct == 0) ptx::mbar_arrive(ptx::smem_u32(kv_empty + ((kv_ctr - 1) % PC_NKV)));
+            if (has_cur && hw == 0) {
+              float s = 0.f;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + wA * ka[i] + (vB ? wB * kb2[i] : 0.f);
+              for (int i = 0; i < 8; ++i) s = fmaf(q[i], sm_cur[sub * 8 + i], s);
+#pragma unroll
+              for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0x0000ffffu, s, off);
+              const float mn = fmaxf(m, s), corr = __expf(m - mn), pw = __expf(s - mn);
+              lsum = lsum * corr + pw;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + pw * sm_cur[128 + sub * 8 + i];
               m = mn;
             }
-          }
-          compute_sync();   // KV tiles fully consumed; sm_cur visible
-          if (npos > 0 && ct == 0) ptx::mbar_arrive(ptx::smem_u32(kv_empty + ((kv_ctr - 1) % PC_NKV)));
-          if (has_cur && hw == 0) {
-            float s = 0.f;
+          },
+          // ---- unit end: merge the 8 half-warp states -> one partial (m, l, o[128]) for split z
+          [&](int r, int h, int z) {
+            if (sub == 0) { sm_m[hw] = m; sm_l[hw] = lsum; }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) s = fmaf(q[i], sm_cur[sub * 8 + i], s);
+            for (int i = 0; i < 8; ++i) sm_o[hw * 128 + sub * 8 + i] = o[i];
+            compute_sync();
+            {
+              float M = -INFINITY;
 #pragma unroll
-            for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0x0000ffffu, s, off);
-            const float mn = fmaxf(m, s), corr = __expf(m - mn), pw = __expf(s - mn);
-            lsum = lsum * corr + pw;
+              for (int i = 0; i < 8; ++i) M = fmaxf(M, sm_m[i]);
+              float Ls = 0.f, O = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + pw * sm_cur[128 + sub * 8 + i];
-            m = mn;
-          }
-          // merge the 8 half-warp states -> one partial (m, l, o[128]) for this chunk
-          if (sub == 0) { sm_m[hw] = m; sm_l[hw] = lsum; }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) sm_o[hw * 128 + sub * 8 + i] = o[i];
-          compute_sync();
-          {
-            float M = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) M = fmaxf(M, sm_m[i]);
-            float Ls = 0.f, O = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (sm_m[i] > -INFINITY) {
-                const float w = __expf(sm_m[i] - M);
-                Ls += sm_l[i] * w;
-                O += sm_o[i * 128 + ct] * w;
-              }
-            const size_t pidx = ((size_t)r * p.H + h) * PC_MAX_CHUNKS + c;
-            p.part_o[pidx * 128 + ct] = O;
-            if (ct == 0) { p.part_ml[pidx * 2] = M; p.part_ml[pidx * 2 + 1] = Ls; }
-          }
-          compute_sync();   // sm_o / sm_m / sm_cur are reused by the next unit
-        });
+              for (int i = 0; i < 8; ++i)
+                if (sm_m[i] > -INFINITY) {
+                  const float w = __expf(sm_m[i] - M);
+                  Ls += sm_l[i] * w;
+                  O += sm_o[i * 128 + ct] * w;
+                }
+              const size_t pidx = ((size_t)r * p.H + h) * PC_MAX_CHUNKS + z;
+              p.part_o[pidx * 128 + ct] = O;
+              if (ct == 0) { p.part_ml[pidx * 2] = M; p.part_ml[pidx * 2 + 1] = Ls; }
+            }
+            compute_sync();   // sm_o / sm_m / sm_cur are reused by the next unit
+          });
       }
       stamp();
       grid_arrive();
@@ -611,7 +632,6 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       // ---- wo + residual: B = merged attention output (columns = this CTA's K range of heads)
       grid_wait();
       stamp();
-      zero_slice(p.qkv, (size_t)PC_RPAD * 3 * p.D);
       if (s_o.nt > 0) {
         const int nchunk = (s_o.kb1 - s_o.kb0) * 8;
         for (int i = ct; i < p.R * nchunk; i += 128) {
@@ -619,7 +639,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           const int k = s_o.kb0 * 64 + c * 8;
           const int h = k >> 7, d0 = k & 127;
           const int u = p.st.slot_map[n >> 1];
-          const int nch = att_chunks(p.st.pos[u] + 1, ppc);
+          const int nch = att_split(p.st.pos[u] + 1, ppc, max(1, G / (p.R * p.H))).nz;
           const size_t pb = ((size_t)n * p.H + h) * PC_MAX_CHUNKS;
           float M = -INFINITY;
           for (int z = 0; z < nch; ++z) M = fmaxf(M, __ldcg(p.part_ml + (pb + z) * 2));
@@ -645,6 +665,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       epilogue(s_o, p.x, p.D, p.D, 1 << 30, nullptr);
       stamp();
       grid_arrive();
+      zero_slice(p.qkv, (size_t)PC_RPAD * 3 * p.D);  // q, k, v were consumed by the attention phase; ordered by the next arrive
 
       // ---- w1 | w3: B = RMSNorm(x) * ffn_norm; out: g | u (zero on entry)
       grid_wait();

@@ -529,12 +529,13 @@ __global__ void __launch_bounds__(SAMP_THREADS) k_sample(SampleP p, S1State st) 
     key[v] = k;
     sid[v] = (unsigned short)v;
   }
+  __syncthreads();
   if (p.decode_mode) {
     // the persistent decode kernel accumulates split-K partial logits with red.add: hand the rows back zeroed
+    // (after the barrier: every thread has consumed its logits by now)
     float* z = const_cast<float*>(lc);
     for (int v = tid; v < 2 * V; v += SAMP_THREADS) z[v] = 0.f;
   }
-  __syncthreads();
 
   // -- ascending bitonic sort of (logit, index); padding (+inf) sinks to the end
   for (int k = 2; k <= SAMP_PAD; k <<= 1) {
