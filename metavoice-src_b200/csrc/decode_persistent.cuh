@@ -29,6 +29,7 @@ constexpr int PC_BKB_MAX = 12;       // k-blocks of B one CTA may own in a phase
 constexpr int PC_NKV = 2;            // (K tile, V tile) slots
 constexpr int PC_MAX_CHUNKS = 64;    // per (row, head): ceil(2048 / 32) in fp32 mode
 constexpr int PC_TRACE_EVENTS = 512;
+constexpr int PC_MAX_TILES = 128;    // attention KV tiles one CTA may own per layer
 
 template <int NB> struct PcCfg {
   static constexpr int STAGES = (NB == 16) ? 8 : 6;
@@ -36,7 +37,8 @@ template <int NB> struct PcCfg {
   static constexpr int RH = NB / 2;                      // activation rows carried (hi rows; lo rows follow)
   static constexpr int TMEM_COLS = (2 * NB < 32) ? 32 : 2 * NB;
   static constexpr size_t SMEM = 1024 + (size_t)STAGES * PC_STAGE_BYTES + B_BYTES + (size_t)PC_NKV * 2 * PC_STAGE_BYTES +
-                                 (2 * STAGES + 1 + 4 + 2 * PC_NKV) * 8 + 16 + (1024 + 8 + 8 + PC_RPAD + 256 + 64) * 4 + 64;
+                                 (2 * STAGES + 1 + 4 + 2 * PC_NKV + 1) * 8 + 16 + (1024 + 8 + 8 + PC_RPAD + 256 + 64) * 4 +
+                                 PC_MAX_TILES * 16 + (PC_RPAD + 4) * 4 + 64;
 };
 
 struct PcMat {     // one weight matrix kind, static decomposition
@@ -144,28 +146,46 @@ __device__ __forceinline__ AttSplit att_split(int L, int ppc, int zmax) {
   a.nz = (a.tt + a.tps - 1) / a.tps;
   return a;
 }
-template <typename FU, typename FT, typename FE>
-__device__ __forceinline__ void for_each_att(const PcParams& p, int cta, int G, int ppc, FU&& unit_begin, FT&& tile, FE&& unit_end) {
+// Per-step attention tile table of this CTA (identical for every layer; only the layer base pointer differs):
+// built once by one thread, walked by the producer (KV loads) and by the compute warps.
+struct AttTile {
+  uint32_t off;     // byte offset of the tile inside one layer's K (or V) region
+  uint32_t meta;    // npos | has_cur << 8 | unit_first << 9 | unit_last << 10 | owns_cur << 11
+  uint32_t where;   // r | h << 8 | z << 16 | cache_row << 24
+  int L;            // positions of the row incl. the current token
+};
+__device__ __forceinline__ int build_att_table(const PcParams& p, int cta, int G, int ppc, int esz, AttTile* tab, int* row_nz) {
   const int zmax = max(1, G / (p.R * p.H));
-  int unit0 = 0;
+  int nt = 0, base = 0;
+  int id = cta;
   for (int r = 0; r < p.R; ++r) {
     const int u = p.st.slot_map[r >> 1];
     const int L = p.st.pos[u] + 1;
     const AttSplit a = att_split(L, ppc, zmax);
-    for (int h = 0; h < p.H; ++h) {
-      const int first = (cta - (unit0 % G) + G) % G;
-      for (int z = first; z < a.nz; z += G) {
-        const int t1 = min(a.tt, (z + 1) * a.tps);
-        unit_begin(r, h, z, L, 2 * u + (r & 1), t1 == a.tt);
-        for (int t = z * a.tps; t < t1; ++t) {
-          const int p0 = t * ppc;
-          tile(r, h, p0, min(L - 1, p0 + ppc) - p0, p0 + ppc >= L, L, 2 * u + (r & 1));
-        }
-        unit_end(r, h, z);
+    row_nz[r] = a.nz;
+    const int units = p.H * a.nz;
+    const int cr = 2 * u + (r & 1);
+    while (id < base + units) {            // this CTA's units inside row r: ids cta, cta+G, ...
+      const int idx = id - base;
+      const int h = idx / a.nz, z = idx - h * a.nz;
+      const int t1 = min(a.tt, (z + 1) * a.tps);
+      for (int t = z * a.tps; t < t1; ++t) {
+        if (nt >= PC_MAX_TILES) __trap();   // fail loudly rather than drop work
+        const int p0 = t * ppc;
+        const int npos = min(L - 1, p0 + ppc) - p0;
+        AttTile e;
+        e.off = (uint32_t)((((size_t)cr * p.H + h) * p.S_max + p0) * 128 * esz);
+        e.meta = (uint32_t)npos | ((p0 + ppc >= L) ? 0x100u : 0u) | ((t == z * a.tps) ? 0x200u : 0u) |
+                 ((t == t1 - 1) ? 0x400u : 0u) | ((t1 == a.tt) ? 0x800u : 0u);
+        e.where = (uint32_t)r | ((uint32_t)h << 8) | ((uint32_t)z << 16) | ((uint32_t)cr << 24);
+        e.L = L;
+        tab[nt++] = e;
       }
-      unit0 += a.nz;
+      id += G;
     }
+    base += units;
   }
+  return nt;
 }
 
 template <bool KV_FP32>
@@ -203,8 +223,11 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* kv_full = acc_empty + 2;
   uint64_t* kv_empty = kv_full + PC_NKV;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + PC_NKV);
+  uint64_t* tab_ready = kv_empty + PC_NKV;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tab_ready + 1);
   float* sm_f = reinterpret_cast<float*>(tmem_slot + 4);
+  AttTile* att_tab = reinterpret_cast<AttTile*>(sm_f + (1024 + 8 + 8 + PC_RPAD + 256 + 64));
+  int* row_nz = reinterpret_cast<int*>(att_tab + PC_MAX_TILES);   // [PC_RPAD] splits per row, then [1] tile count
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x, G = gridDim.x;
@@ -225,6 +248,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       ptx::mbar_init(ptx::smem_u32(kv_full + i), 1);
       ptx::mbar_init(ptx::smem_u32(kv_empty + i), 1);
     }
+    ptx::mbar_init(ptx::smem_u32(tab_ready), 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -264,33 +288,34 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           }
         }
       };
-      // KV tiles [from, to) (in this CTA's tile order) of layer l; positions < pos come from earlier steps
+      // KV tiles [from, to) (in this CTA's table order) of layer l; positions < pos come from earlier steps
       auto kv_units = [&](int l, int from, int to) {
         const char* kbase = p.kv + (size_t)l * 2 * p.kv_half;
         const char* vbase = kbase + p.kv_half;
+        const int n_tiles = row_nz[PC_RPAD];
         int idx = 0;
-        for_each_att(p, cta, G, ppc, [&](int, int, int, int, int, bool) {},
-                     [&](int r, int h, int p0, int npos, bool, int, int cr) {
-                       if (npos <= 0) return;               // only the current position: it comes from registers
-                       const int my = idx++;
-                       if (my < from || my >= to) return;
-                       const uint32_t ks = kv_ctr % PC_NKV, ph = (kv_ctr / PC_NKV) & 1u;
-                       ++kv_ctr;
-                       ptx::mbar_wait(ptx::smem_u32(kv_empty + ks), ph ^ 1u);
-                       const size_t off = (((size_t)cr * p.H + h) * p.S_max + p0) * 128 * esz;
-                       const uint32_t bytes = (uint32_t)npos * 128 * esz;
-                       const uint32_t full = ptx::smem_u32(kv_full + ks);
-                       ptx::mbar_arrive_expect_tx(full, 2 * bytes);
-                       uint8_t* dst = kvbuf + (size_t)ks * 2 * PC_STAGE_BYTES;
-                       bulk_load(ptx::smem_u32(dst), kbase + off, bytes, full);
-                       bulk_load(ptx::smem_u32(dst + PC_STAGE_BYTES), vbase + off, bytes, full);
-                     },
-                     [&](int, int, int) {});
+        for (int i = 0; i < n_tiles; ++i) {
+          const AttTile e = att_tab[i];
+          const int npos = (int)(e.meta & 0xffu);
+          if (npos == 0) continue;                 // only the current position: it comes from registers
+          const int my = idx++;
+          if (my < from) continue;
+          if (my >= to) break;
+          const uint32_t ks = kv_ctr % PC_NKV, ph = (kv_ctr / PC_NKV) & 1u;
+          ++kv_ctr;
+          ptx::mbar_wait(ptx::smem_u32(kv_empty + ks), ph ^ 1u);
+          const uint32_t bytes = (uint32_t)npos * 128 * esz;
+          const uint32_t full = ptx::smem_u32(kv_full + ks);
+          ptx::mbar_arrive_expect_tx(full, 2 * bytes);
+          uint8_t* dst = kvbuf + (size_t)ks * 2 * PC_STAGE_BYTES;
+          bulk_load(ptx::smem_u32(dst), kbase + e.off, bytes, full);
+          bulk_load(ptx::smem_u32(dst + PC_STAGE_BYTES), vbase + e.off, bytes, full);
+        }
       };
       for (int l = 0; l < p.n_layer; ++l) {
         if (l == 0) {
           gemm_tiles(&tm_qkv, &tm_qkv, 1 << 30, s_qkv, 0);   // weights first: they need nothing from the previous kernel
-          pdl_wait();                                         // pos[] is written by the previous sampler kernel
+          ptx::mbar_wait(ptx::smem_u32(tab_ready), 0);        // tile table built (after the PDL wait) by the compute warps
           kv_units(0, 0, 1 << 30);
         } else {
           kv_units(l, PC_NKV, 1 << 30);                       // (units beyond the prefetched ones)
@@ -357,6 +382,11 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     float* sm_red = sm_cur + 256;       // [PC_RPAD][4] partial sums of squares
     uint32_t tile_ctr = 0, bar_idx = 0, kv_ctr = 0;
     pdl_wait();                         // state / x inputs of the previous kernels are visible
+    if (ct == 0) {
+      row_nz[PC_RPAD] = build_att_table(p, cta, G, ppc, esz, att_tab, row_nz);
+      ptx::mbar_arrive(ptx::smem_u32(tab_ready));   // release: the producer may walk the table
+    }
+    compute_sync();
     int ev = 0;
     auto stamp = [&]() {
       if (p.trace != nullptr && ct == 0 && ev < PC_TRACE_EVENTS) p.trace[(size_t)cta * PC_TRACE_EVENTS + ev] = clock64();
@@ -518,9 +548,16 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         const int hw = cw * 2 + half;               // half-warp id 0..7
         const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
         float q[8], o[8], m = -INFINITY, lsum = 0.f, kcur = 0.f, vcur = 0.f;
-        for_each_att(p, cta, G, ppc,
-          // ---- unit begin: one round trip for everything the unit needs from global memory
-          [&](int r, int h, int z, int L, int cr, bool owns_cur) {
+        const int n_tiles = row_nz[PC_RPAD];
+        for (int ti = 0; ti < n_tiles; ++ti) {
+          const AttTile e = att_tab[ti];
+          const int npos = (int)(e.meta & 0xffu);
+          const bool has_cur = e.meta & 0x100u, unit_first = e.meta & 0x200u, unit_last = e.meta & 0x400u,
+                     owns_cur = e.meta & 0x800u;
+          const int r = e.where & 0xff, h = (e.where >> 8) & 0xff, z = (e.where >> 16) & 0xff, cr = e.where >> 24;
+          const int L = e.L;
+          if (unit_first) {
+            // ---- unit begin: one round trip for everything the unit needs from global memory
             const float* qrow = p.qkv + (size_t)r * 3 * p.D + h * 128;
             const float4 qa = __ldcg(reinterpret_cast<const float4*>(qrow + sub * 8));
             const float4 qb = __ldcg(reinterpret_cast<const float4*>(qrow + sub * 8) + 1);
@@ -534,75 +571,73 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             m = -INFINITY; lsum = 0.f;
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = 0.f;
-          },
+          }
           // ---- one KV tile (and, on the row's last tile, the current token)
-          [&](int r, int h, int p0, int npos, bool has_cur, int L, int cr) {
-            if (has_cur) {
-              // append the new token's k, v to the cache, rounded as the cache stores them; share them via smem
-              const size_t e = (((size_t)cr * p.H + h) * p.S_max + (L - 1)) * 128 + ct;
-              if (KV_FP32) {
-                reinterpret_cast<float*>(kbase)[e] = kcur;
-                reinterpret_cast<float*>(vbase)[e] = vcur;
-              } else {
-                const __nv_bfloat16 kb16 = __float2bfloat16_rn(kcur), vb16 = __float2bfloat16_rn(vcur);
-                reinterpret_cast<__nv_bfloat16*>(kbase)[e] = kb16;
-                reinterpret_cast<__nv_bfloat16*>(vbase)[e] = vb16;
-                kcur = __bfloat162float(kb16);
-                vcur = __bfloat162float(vb16);
-              }
-              sm_cur[ct] = kcur;
-              sm_cur[128 + ct] = vcur;
+          if (has_cur) {
+            // append the new token's k, v to the cache, rounded as the cache stores them; share them via smem
+            const size_t ce = (((size_t)cr * p.H + h) * p.S_max + (L - 1)) * 128 + ct;
+            if (KV_FP32) {
+              reinterpret_cast<float*>(kbase)[ce] = kcur;
+              reinterpret_cast<float*>(vbase)[ce] = vcur;
+            } else {
+              const __nv_bfloat16 kb16 = __float2bfloat16_rn(kcur), vb16 = __float2bfloat16_rn(vcur);
+              reinterpret_cast<__nv_bfloat16*>(kbase)[ce] = kb16;
+              reinterpret_cast<__nv_bfloat16*>(vbase)[ce] = vb16;
+              kcur = __bfloat162float(kb16);
+              vcur = __bfloat162float(vb16);
             }
-            if (npos > 0) {
-              const uint32_t ks = kv_ctr % PC_NKV, ph = (kv_ctr / PC_NKV) & 1u;
-              ++kv_ctr;
-              ptx::mbar_wait(ptx::smem_u32(kv_full + ks), ph);
-              const uint8_t* kt = kvbuf + (size_t)ks * 2 * PC_STAGE_BYTES;
-              const uint8_t* vt = kt + PC_STAGE_BYTES;
-              // each half-warp owns positions hw, hw+8, ...; two positions per trip for ILP
-              for (int pb = hw; pb < npos; pb += 16) {
-                const int pA = pb, pB = pb + 8;
-                const bool vB = pB < npos;
-                float ka[8], kb2[8], sA = 0.f, sB = 0.f;
-                load8s<KV_FP32>(kt, pA, sub, ka);
-                if (vB) load8s<KV_FP32>(kt, pB, sub, kb2);
+            sm_cur[ct] = kcur;
+            sm_cur[128 + ct] = vcur;
+          }
+          if (npos > 0) {
+            const uint32_t ks = kv_ctr % PC_NKV, ph = (kv_ctr / PC_NKV) & 1u;
+            ++kv_ctr;
+            ptx::mbar_wait(ptx::smem_u32(kv_full + ks), ph);
+            const uint8_t* kt = kvbuf + (size_t)ks * 2 * PC_STAGE_BYTES;
+            const uint8_t* vt = kt + PC_STAGE_BYTES;
+            // each half-warp owns positions hw, hw+8, ...; two positions per trip for ILP
+            for (int pb = hw; pb < npos; pb += 16) {
+              const int pA = pb, pB = pb + 8;
+              const bool vB = pB < npos;
+              float ka[8], kb2[8], sA = 0.f, sB = 0.f;
+              load8s<KV_FP32>(kt, pA, sub, ka);
+              if (vB) load8s<KV_FP32>(kt, pB, sub, kb2);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  sA = fmaf(q[i], ka[i], sA);
-                  if (vB) sB = fmaf(q[i], kb2[i], sB);
-                }
-#pragma unroll
-                for (int off = 8; off > 0; off >>= 1) {   // reduce inside the 16-lane group only: trip counts differ per half-warp
-                  sA += __shfl_xor_sync(hmask, sA, off);
-                  sB += __shfl_xor_sync(hmask, sB, off);
-                }
-                load8s<KV_FP32>(vt, pA, sub, ka);
-                if (vB) load8s<KV_FP32>(vt, pB, sub, kb2);
-                const float mn = fmaxf(m, vB ? fmaxf(sA, sB) : sA);
-                const float corr = __expf(m - mn), wA = __expf(sA - mn), wB = vB ? __expf(sB - mn) : 0.f;
-                lsum = lsum * corr + wA + wB;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + wA * ka[i] + (vB ? wB * kb2[i] : 0.f);
-                m = mn;
+              for (int i = 0; i < 8; ++i) {
+                sA = fmaf(q[i], ka[i], sA);
+                if (vB) sB = fmaf(q[i], kb2[i], sB);
               }
-            }
-            if (npos > 0 || has_cur) compute_sync();   // KV tile fully consumed; sm_cur visible
-            if (npos > 0 && ct == 0) ptx::mbar_arrive(ptx::smem_u32(kv_empty + ((kv_ctr - 1) % PC_NKV)));
-            if (has_cur && hw == 0) {
-              float s = 0.f;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) s = fmaf(q[i], sm_cur[sub * 8 + i], s);
+              for (int off = 8; off > 0; off >>= 1) {   // reduce inside the 16-lane group only: trip counts differ per half-warp
+                sA += __shfl_xor_sync(hmask, sA, off);
+                sB += __shfl_xor_sync(hmask, sB, off);
+              }
+              load8s<KV_FP32>(vt, pA, sub, ka);
+              if (vB) load8s<KV_FP32>(vt, pB, sub, kb2);
+              const float mn = fmaxf(m, vB ? fmaxf(sA, sB) : sA);
+              const float corr = __expf(m - mn), wA = __expf(sA - mn), wB = vB ? __expf(sB - mn) : 0.f;
+              lsum = lsum * corr + wA + wB;
 #pragma unroll
-              for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0x0000ffffu, s, off);
-              const float mn = fmaxf(m, s), corr = __expf(m - mn), pw = __expf(s - mn);
-              lsum = lsum * corr + pw;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + pw * sm_cur[128 + sub * 8 + i];
+              for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + wA * ka[i] + (vB ? wB * kb2[i] : 0.f);
               m = mn;
             }
-          },
-          // ---- unit end: merge the 8 half-warp states -> one partial (m, l, o[128]) for split z
-          [&](int r, int h, int z) {
+          }
+          if (npos > 0 || has_cur) compute_sync();   // KV tile fully consumed; sm_cur visible
+          if (npos > 0 && ct == 0) ptx::mbar_arrive(ptx::smem_u32(kv_empty + ((kv_ctr - 1) % PC_NKV)));
+          if (has_cur && hw == 0) {
+            float sdot = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sdot = fmaf(q[i], sm_cur[sub * 8 + i], sdot);
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) sdot += __shfl_xor_sync(0x0000ffffu, sdot, off);
+            const float mn = fmaxf(m, sdot), corr = __expf(m - mn), pw = __expf(sdot - mn);
+            lsum = lsum * corr + pw;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + pw * sm_cur[128 + sub * 8 + i];
+            m = mn;
+          }
+          if (unit_last) {
+            // ---- unit end: merge the 8 half-warp states -> one partial (m, l, o[128]) for split z
             if (sub == 0) { sm_m[hw] = m; sm_l[hw] = lsum; }
 #pragma unroll
             for (int i = 0; i < 8; ++i) sm_o[hw * 128 + sub * 8 + i] = o[i];
@@ -624,7 +659,8 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
               if (ct == 0) { p.part_ml[pidx * 2] = M; p.part_ml[pidx * 2 + 1] = Ls; }
             }
             compute_sync();   // sm_o / sm_m / sm_cur are reused by the next unit
-          });
+          }
+        }
       }
       stamp();
       grid_arrive();
@@ -638,8 +674,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           const int n = i / nchunk, c = i - n * nchunk;
           const int k = s_o.kb0 * 64 + c * 8;
           const int h = k >> 7, d0 = k & 127;
-          const int u = p.st.slot_map[n >> 1];
-          const int nch = att_split(p.st.pos[u] + 1, ppc, max(1, G / (p.R * p.H))).nz;
+          const int nch = row_nz[n];
           const size_t pb = ((size_t)n * p.H + h) * PC_MAX_CHUNKS;
           float M = -INFINITY;
           for (int z = 0; z < nch; ++z) M = fmaxf(M, __ldcg(p.part_ml + (pb + z) * 2));
