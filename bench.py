@@ -8,7 +8,7 @@ top_p 0.95, guidance 3.0, temperature 1.0, bf16 weights + bf16 KV cache) on ever
   value  : whole-job stage-1 tokens/s with inputs already resident in HBM (prefill + decode on device)
   e2e    : same metric through the reference-facing plugin call mvb_s1_generate with HOST buffers
            (prompt/speaker host->device, tokens device->host inside the timed region)
-  roofline: the decode step (one CUDA graph replay), algorithmic bytes / CUDA-event time vs measured HBM peak
+  roofline: the decode step (persistent fused kernel + sampler), algorithmic bytes / CUDA-event time vs measured HBM peak
   cpu_baseline: the oracle port of the reference's CPU path, timed on this box's host cores (bounded sample)
 
 `--impl reference` times the reference's CPU implementation (oracle port; the Python reference cannot travel
@@ -256,7 +256,7 @@ def main():
         "e2e": {"value": round(e2e_toks * world / (e2e_ms_max * 1e-3), 2), "unit": "tokens/s",
                 "h2d_bytes_per_step": int(utts * (T_PROMPT * 4 * 2 + 256 * 4 + 32)), "d2h_bytes_per_step": int(utts * (N_NEW * 4 + 8))},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "decode step (one CUDA-graph replay: 24x{qkv,attn,wo,w13,w2} + head) + sampler",
+        "roofline": {"bound": "hbm", "kernel": "k_decode_persistent (one persistent kernel per token: 24 x {qkv, attention, wo, w1|w3, w2} + head) + k_sample",
                      "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": None, "bytes_per_launch": int(step_bytes),
                      "ms_per_launch": round(step_ms, 4), "context_len": L_mid},

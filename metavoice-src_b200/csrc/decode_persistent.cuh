@@ -50,6 +50,7 @@ struct PcMat {     // one weight matrix kind, static decomposition
 
 struct PcParams {
   int n_layer, D, F, V, H, S_max, R, n_utts, kv_fp32;
+  int a_sw32;      // weight tiles staged as 4 x [128 x 16] sub-tiles (32B swizzle) instead of one [128 x 64] (128B swizzle)
   float eps;
   PcMat m_qkv, m_o, m_w13, m_w2, m_head;
   const __nv_bfloat16* attn_norm;   // layer 0; layer l at + l * layer_stride
@@ -284,7 +285,13 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             ptx::mbar_wait(ptx::smem_u32(b_empty + s), ph ^ 1u);
             const uint32_t full = ptx::smem_u32(b_full + s);
             ptx::mbar_arrive_expect_tx(full, PC_STAGE_BYTES);
-            tma_load_3d(ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES), tm, full, kb * 64, tt * 128, layer, pol);
+            const uint32_t dst = ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES);
+            if (p.a_sw32) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) tma_load_3d(dst + 4096 * j, tm, full, kb * 64 + 16 * j, tt * 128, layer, pol);
+            } else {
+              tma_load_3d(dst, tm, full, kb * 64, tt * 128, layer, pol);
+            }
           }
         }
       };
@@ -350,11 +357,18 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             ++slot;
             ptx::mbar_wait(ptx::smem_u32(b_full + s), ph);
             ptx::tc_fence_after();
-            const uint64_t ad = ptx::umma_desc_k_sw128(ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES));
+            const uint32_t a_addr = ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES);
+            const uint64_t ad = ptx::umma_desc_k_sw128(a_addr);
             const uint64_t bd = ptx::umma_desc_k_sw128(ptx::smem_u32(Bop + (size_t)(kb - sl.kb0) * (NB * 128)));
+            if (p.a_sw32) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::umma_bf16(dcol, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb != sl.kb0) || k != 0));
+              for (int k = 0; k < 4; ++k)
+                ptx::umma_bf16(dcol, ptx::umma_desc_k_sw32(a_addr + 4096 * k), bd + 2 * k, idesc, (uint32_t)((kb != sl.kb0) || k != 0));
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ptx::umma_bf16(dcol, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb != sl.kb0) || k != 0));
+            }
             ptx::umma_commit(ptx::smem_u32(b_empty + s));
           }
           ptx::umma_commit(ptx::smem_u32(acc_full + ab));
@@ -420,8 +434,9 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       if (sl.nt == 0) return;
       const int nchunk = (sl.kb1 - sl.kb0) * 8;
       const int total = p.R * nchunk;
-      constexpr int MAXC = 3;             // chunks pre-loaded per thread (covers R = 2 completely)
+      constexpr int MAXC = 2;             // chunks pre-loaded per thread (covers R = 2 completely: 176 chunks)
       float4 ca[MAXC], cb[MAXC];
+      uint4 cg[MAXC];
 #pragma unroll
       for (int j = 0; j < MAXC; ++j) {
         const int i = ct + j * 128;
@@ -430,6 +445,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)n * p.D + sl.kb0 * 64 + c * 8);
           ca[j] = __ldcg(xr);
           cb[j] = __ldcg(xr + 1);
+          cg[j] = *reinterpret_cast<const uint4*>(gain + sl.kb0 * 64 + c * 8);
         }
       }
       const int f4_per_row = p.D >> 2;
@@ -459,10 +475,8 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         sm_rs[ct] = rsqrtf(t / (float)p.D + p.eps);
       }
       compute_sync();
-      auto emit = [&](int i, const float4& a, const float4& b) {
+      auto emit = [&](int i, const float4& a, const float4& b, const uint4& gw) {
         const int n = i / nchunk, c = i - n * nchunk;
-        const int k = sl.kb0 * 64 + c * 8;
-        const uint4 gw = *reinterpret_cast<const uint4*>(gain + k);
         const float rs = sm_rs[n];
         float v[8] = {(a.x * rs) * bf_lo(gw.x), (a.y * rs) * bf_hi(gw.x), (a.z * rs) * bf_lo(gw.y), (a.w * rs) * bf_hi(gw.y),
                       (b.x * rs) * bf_lo(gw.z), (b.y * rs) * bf_hi(gw.z), (b.z * rs) * bf_lo(gw.w), (b.w * rs) * bf_hi(gw.w)};
@@ -470,11 +484,25 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       };
 #pragma unroll
       for (int j = 0; j < MAXC; ++j)
-        if (ct + j * 128 < total) emit(ct + j * 128, ca[j], cb[j]);
-      for (int i = ct + MAXC * 128; i < total; i += 128) {
-        const int n = i / nchunk, c = i - n * nchunk;
-        const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)n * p.D + sl.kb0 * 64 + c * 8);
-        emit(i, __ldcg(xr), __ldcg(xr + 1));
+        if (ct + j * 128 < total) emit(ct + j * 128, ca[j], cb[j], cg[j]);
+      // larger batches: 2 chunks (6 loads) in flight per thread per trip
+      for (int i0 = ct + MAXC * 128; i0 < total; i0 += 2 * 128) {
+        float4 la[2], lb[2];
+        uint4 lg[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int i = i0 + j * 128;
+          if (i < total) {
+            const int n = i / nchunk, c = i - n * nchunk;
+            const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)n * p.D + sl.kb0 * 64 + c * 8);
+            la[j] = __ldcg(xr);
+            lb[j] = __ldcg(xr + 1);
+            lg[j] = *reinterpret_cast<const uint4*>(gain + sl.kb0 * 64 + c * 8);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          if (i0 + j * 128 < total) emit(i0 + j * 128, la[j], lb[j], lg[j]);
       }
       b_publish();
     };
@@ -677,17 +705,42 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           const int nch = row_nz[n];
           const size_t pb = ((size_t)n * p.H + h) * PC_MAX_CHUNKS;
           float M = -INFINITY;
-          for (int z = 0; z < nch; ++z) M = fmaxf(M, __ldcg(p.part_ml + (pb + z) * 2));
           float den = 0.f, v[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) v[e] = 0.f;
-          for (int z = 0; z < nch; ++z) {
-            const float w = __expf(__ldcg(p.part_ml + (pb + z) * 2) - M);
-            den += __ldcg(p.part_ml + (pb + z) * 2 + 1) * w;
-            const float4* po = reinterpret_cast<const float4*>(p.part_o + (pb + z) * 128 + d0);
-            const float4 a = __ldcg(po), b = __ldcg(po + 1);
-            v[0] += a.x * w; v[1] += a.y * w; v[2] += a.z * w; v[3] += a.w * w;
-            v[4] += b.x * w; v[5] += b.y * w; v[6] += b.z * w; v[7] += b.w * w;
+          if (nch <= 4) {
+            // one round trip: (m, l) and o of every split are requested together
+            float2 ml[4];
+            float4 oa[4], ob[4];
+#pragma unroll
+            for (int z = 0; z < 4; ++z)
+              if (z < nch) {
+                ml[z] = __ldcg(reinterpret_cast<const float2*>(p.part_ml + (pb + z) * 2));
+                const float4* po = reinterpret_cast<const float4*>(p.part_o + (pb + z) * 128 + d0);
+                oa[z] = __ldcg(po);
+                ob[z] = __ldcg(po + 1);
+              }
+#pragma unroll
+            for (int z = 0; z < 4; ++z)
+              if (z < nch) M = fmaxf(M, ml[z].x);
+#pragma unroll
+            for (int z = 0; z < 4; ++z)
+              if (z < nch) {
+                const float w = __expf(ml[z].x - M);
+                den += ml[z].y * w;
+                v[0] += oa[z].x * w; v[1] += oa[z].y * w; v[2] += oa[z].z * w; v[3] += oa[z].w * w;
+                v[4] += ob[z].x * w; v[5] += ob[z].y * w; v[6] += ob[z].z * w; v[7] += ob[z].w * w;
+              }
+          } else {
+            for (int z = 0; z < nch; ++z) M = fmaxf(M, __ldcg(p.part_ml + (pb + z) * 2));
+            for (int z = 0; z < nch; ++z) {
+              const float w = __expf(__ldcg(p.part_ml + (pb + z) * 2) - M);
+              den += __ldcg(p.part_ml + (pb + z) * 2 + 1) * w;
+              const float4* po = reinterpret_cast<const float4*>(p.part_o + (pb + z) * 128 + d0);
+              const float4 a = __ldcg(po), b = __ldcg(po + 1);
+              v[0] += a.x * w; v[1] += a.y * w; v[2] += a.z * w; v[3] += a.w * w;
+              v[4] += b.x * w; v[5] += b.y * w; v[6] += b.z * w; v[7] += b.w * w;
+            }
           }
           const float inv = 1.f / den;
 #pragma unroll
@@ -716,18 +769,33 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       stamp();
       if (s_w2.nt > 0) {
         const int nchunk = (s_w2.kb1 - s_w2.kb0) * 8;
-        for (int i = ct; i < p.R * nchunk; i += 128) {
-          const int n = i / nchunk, c = i - n * nchunk;
-          const int k = s_w2.kb0 * 64 + c * 8;
-          const float4* gp = reinterpret_cast<const float4*>(p.gu + (size_t)n * 2 * p.F + k);
-          const float4* up = reinterpret_cast<const float4*>(p.gu + (size_t)n * 2 * p.F + p.F + k);
-          const float4 g0 = __ldcg(gp), g1 = __ldcg(gp + 1), u0 = __ldcg(up), u1 = __ldcg(up + 1);
-          const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-          const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-          float v[8];
+        const int total = p.R * nchunk;
+        for (int i0 = ct; i0 < total; i0 += 2 * 128) {
+          float4 g0[2], g1[2], u0[2], u1[2];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = (g[e] / (1.f + expf(-g[e]))) * uu[e];
-          b_store8<NB>(Bop, c >> 3, n, c & 7, v);
+          for (int j = 0; j < 2; ++j) {
+            const int i = i0 + j * 128;
+            if (i < total) {
+              const int n = i / nchunk, c = i - n * nchunk;
+              const int k = s_w2.kb0 * 64 + c * 8;
+              const float4* gp = reinterpret_cast<const float4*>(p.gu + (size_t)n * 2 * p.F + k);
+              const float4* up = reinterpret_cast<const float4*>(p.gu + (size_t)n * 2 * p.F + p.F + k);
+              g0[j] = __ldcg(gp); g1[j] = __ldcg(gp + 1); u0[j] = __ldcg(up); u1[j] = __ldcg(up + 1);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int i = i0 + j * 128;
+            if (i < total) {
+              const int n = i / nchunk, c = i - n * nchunk;
+              const float g[8] = {g0[j].x, g0[j].y, g0[j].z, g0[j].w, g1[j].x, g1[j].y, g1[j].z, g1[j].w};
+              const float uu[8] = {u0[j].x, u0[j].y, u0[j].z, u0[j].w, u1[j].x, u1[j].y, u1[j].z, u1[j].w};
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = (g[e] / (1.f + __expf(-g[e]))) * uu[e];
+              b_store8<NB>(Bop, c >> 3, n, c & 7, v);
+            }
+          }
         }
         b_publish();
       }

@@ -150,6 +150,7 @@ struct mvb_s1 {
   bool path_c = true;
   bool pc_ok = false;
   bool trace = false;
+  bool a_sw32 = false;
   CUtensorMap tm3[6];                                 // 3-D (k, row, layer) maps: wqkv, wo, w1, w3, w2, head
   PcMat pm[5];
   size_t layer_stride_elems = 0;
@@ -166,16 +167,17 @@ struct mvb_s1 {
 
 
 // 3-D tensor map over one matrix kind of every layer: dims {K, M, n_layer}, tile {64, 128, 1}, 128B swizzle.
-static bool make_tmap_bf16_3d(CUtensorMap* tm, const void* ptr, uint64_t K, uint64_t M, uint64_t L, uint64_t layer_stride_bytes) {
+static bool make_tmap_bf16_3d(CUtensorMap* tm, const void* ptr, uint64_t K, uint64_t M, uint64_t L, uint64_t layer_stride_bytes,
+                              bool sw32 = false) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   cuuint64_t dims[3] = {K, M, L};
   cuuint64_t strides[2] = {K * 2, layer_stride_bytes};
-  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t box[3] = {sw32 ? 16u : 64u, 128, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            CU_TENSOR_MAP_INTERLEAVE_NONE, sw32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Static decomposition of one matrix over `ctas` CTAs: the K split that minimises the busiest CTA's k-blocks.
@@ -283,6 +285,7 @@ extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size
   }
   if (const char* e = getenv("MVB_PATHC")) h->path_c = atoi(e) != 0;
   if (const char* e = getenv("MVB_PC_TRACE")) h->trace = atoi(e) != 0;
+  if (const char* e = getenv("MVB_A_SW32")) h->a_sw32 = atoi(e) != 0;
   {
     // persistent decode kernel: needs a uniform layer stride (true for arenas packed in checkpoint order)
     const int D = cfg->dim, F = cfg->intermediate, V = cfg->vocab;
@@ -295,12 +298,12 @@ extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size
     ok = ok && (stride % 16 == 0);
     h->layer_stride_elems = stride / 2;
     const uint64_t NL = cfg->n_layer;
-    ok = ok && make_tmap_bf16_3d(&h->tm3[0], h->lw(0, 1), D, 3 * D, NL, stride);
-    ok = ok && make_tmap_bf16_3d(&h->tm3[1], h->lw(0, 2), D, D, NL, stride);
-    ok = ok && make_tmap_bf16_3d(&h->tm3[2], h->lw(0, 4), D, F, NL, stride);
-    ok = ok && make_tmap_bf16_3d(&h->tm3[3], h->lw(0, 5), D, F, NL, stride);
-    ok = ok && make_tmap_bf16_3d(&h->tm3[4], h->lw(0, 6), F, D, NL, stride);
-    ok = ok && make_tmap_bf16_3d(&h->tm3[5], h->w(4), D, V, 1, (uint64_t)V * D * 2);
+    ok = ok && make_tmap_bf16_3d(&h->tm3[0], h->lw(0, 1), D, 3 * D, NL, stride, h->a_sw32);
+    ok = ok && make_tmap_bf16_3d(&h->tm3[1], h->lw(0, 2), D, D, NL, stride, h->a_sw32);
+    ok = ok && make_tmap_bf16_3d(&h->tm3[2], h->lw(0, 4), D, F, NL, stride, h->a_sw32);
+    ok = ok && make_tmap_bf16_3d(&h->tm3[3], h->lw(0, 5), D, F, NL, stride, h->a_sw32);
+    ok = ok && make_tmap_bf16_3d(&h->tm3[4], h->lw(0, 6), F, D, NL, stride, h->a_sw32);
+    ok = ok && make_tmap_bf16_3d(&h->tm3[5], h->w(4), D, V, 1, (uint64_t)V * D * 2, h->a_sw32);
     h->pm[0] = plan_pc(3 * D, D, h->n_sm);
     h->pm[1] = plan_pc(D, D, h->n_sm);
     h->pm[2] = plan_pc(2 * F, D, h->n_sm);
@@ -510,6 +513,7 @@ static int launch_persistent(mvb_s1* h, cudaStream_t s, int n_utts) {
   const mvb_s1_config& c = h->cfg;
   PcParams p{};
   p.n_layer = c.n_layer; p.D = c.dim; p.F = c.intermediate; p.V = c.vocab; p.H = c.n_head; p.S_max = c.block_size;
+  p.a_sw32 = h->a_sw32 ? 1 : 0;
   p.R = 2 * n_utts; p.n_utts = n_utts; p.kv_fp32 = c.kv_dtype == MVB_KV_FP32; p.eps = c.norm_eps;
   p.m_qkv = h->pm[0]; p.m_o = h->pm[1]; p.m_w13 = h->pm[2]; p.m_w2 = h->pm[3]; p.m_head = h->pm[4];
   p.attn_norm = h->lw(0, 0); p.ffn_norm = h->lw(0, 3); p.out_norm = h->w(3);

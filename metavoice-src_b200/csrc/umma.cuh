@@ -104,6 +104,13 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   const uint64_t hi = (uint64_t)(1024u >> 4) | (1ull << 14) | (2ull << 29);
   return lo | (hi << 32);
 }
+// Same, for a tile stored as [rows][16] bf16 (32 B per row, one UMMA K step) with the 32-byte swizzle
+// (CU_TENSOR_MAP_SWIZZLE_32B): 8-row groups are 256 B apart, so one MMA reads a dense 4 KB block.
+__device__ __forceinline__ uint64_t umma_desc_k_sw32(uint32_t smem_addr) {
+  const uint64_t lo = (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16);
+  const uint64_t hi = (uint64_t)(256u >> 4) | (1ull << 14) | (6ull << 29);
+  return lo | (hi << 32);
+}
 // Instruction descriptor: D=f32, A=B=bf16, both K-major, shape M x N x 16.
 //   [4,6) D fmt (1=f32) | [7,10) A fmt (1=bf16) | [10,13) B fmt | bit15/16 majors (0=K) | [17,23) N>>3 | [24,29) M>>4
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {

@@ -29,7 +29,8 @@ for item in spec.split(","):
     n = int(n)
     os.environ["MVB_PDL"] = "0" if kind.endswith("0") else "1"
     os.environ["MVB_DECODE_B_MIN"] = "1" if kind.startswith("B") else "9999"
-    os.environ["MVB_PATHC"] = "1" if kind.startswith("C") else "0"
+    os.environ["MVB_PATHC"] = "1" if kind[0] in "CS" else "0"
+    os.environ["MVB_A_SW32"] = "1" if kind.startswith("S") else "0"
     m = Transformer(cfg, arena, offsets, device=dev)
     m.setup_caches(2 * n, cfg.block_size, kv_dtype="bf16")
     lib, h, st = m._lib, m.handle, m._stream()
