@@ -146,6 +146,39 @@ int mvb_linear(const void* d_W, int32_t M, int32_t K, const float* d_x, int32_t 
                const void* d_gain, float eps, int32_t split_lo, int32_t ksplit_override, float* d_out,
                int32_t ldo, int32_t accumulate, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Stage 2: the non-causal codebook-expansion model (fam/llm/model.py:195-314 with causal=False) and its sampler
+ * (fam/llm/mixins/non_causal.py:15-67).  Shapes come from second_stage.pt["model_args"] (inference.py:124-128).
+ * Supported: norm_type "rmsnorm", nonlinearity "swiglu", bias False, head size 64 or 128 (anything else fails loudly). */
+typedef struct mvb_s2_config {
+  int32_t n_layer, n_head, n_embd;
+  int32_t hidden;          /* SwiGLU width (layers.py:51-53) */
+  int32_t block_size;      /* sequence length t of the single non-causal pass (non_causal.py:31) */
+  int32_t n_in;            /* input hierarchies (2) */
+  int32_t vocab_in[8];
+  int32_t n_out;           /* predicted hierarchies (6) */
+  int32_t vocab_out[8];
+  int32_t spk_dim;
+  float   norm_eps;
+  int32_t max_batch;
+} mvb_s2_config;
+typedef struct mvb_s2 mvb_s2;
+
+size_t mvb_s2_workspace_bytes(const mvb_s2_config* cfg);
+/* offsets (host): wte[n_in], wpe, speaker_cond_pos, ln_f, lm_heads[n_out], then per layer
+ * {ln_1, attn.c_attn, attn.c_proj, ln_2, mlp.swiglu.w1, mlp.swiglu.w3, mlp.c_proj}; bf16 arena as for stage 1.
+ * d_workspace must be zero-filled.  Replaces Model._init_model (inference.py:102-141). */
+int mvb_s2_create(const mvb_s2_config* cfg, const void* d_arena, size_t arena_bytes, const uint64_t* offsets,
+                  void* d_workspace, mvb_s2** out);
+int mvb_s2_destroy(mvb_s2* h);
+/* == GPT.generate -> _non_causal_sample for `batch` rows: d_idx int32 [batch, n_in, block_size] (built as
+ * inference.py:283-306), d_spk fp32 [batch, spk_dim] or NULL, top_k <= 0 disables, d_noise fp32
+ * [n_out, batch*block_size, vocab_out] = the Exp(1) draws torch.multinomial consumes (NULL = on-device Philox),
+ * d_tokens int32 [batch, n_out, block_size]; d_logits_out optional fp32 [n_out, batch*block_size, vocab_out]. */
+int mvb_s2_forward(mvb_s2* h, int32_t batch, const int32_t* d_idx, const float* d_spk, float temperature,
+                   int32_t top_k, const float* d_noise, uint64_t seed, int32_t* d_tokens, float* d_logits_out,
+                   void* stream);
+
 #define MVB_OK 0
 #define MVB_ERR_CUDA 1
 #define MVB_ERR_ARG 2

@@ -25,6 +25,12 @@ class Sampling(C.Structure):
                 ("top_k", C.c_int32), ("end_of_audio", C.c_int32), ("seed", C.c_uint64)]
 
 
+class S2Config(C.Structure):
+    _fields_ = [("n_layer", C.c_int32), ("n_head", C.c_int32), ("n_embd", C.c_int32), ("hidden", C.c_int32),
+                ("block_size", C.c_int32), ("n_in", C.c_int32), ("vocab_in", C.c_int32 * 8), ("n_out", C.c_int32),
+                ("vocab_out", C.c_int32 * 8), ("spk_dim", C.c_int32), ("norm_eps", C.c_float), ("max_batch", C.c_int32)]
+
+
 # name -> (restype, argtypes); also the list the symbol-export test checks against include/mvb200.h
 SIGNATURES = {
     "mvb_abi_version": (C.c_int, []),
@@ -48,6 +54,12 @@ SIGNATURES = {
                                C.POINTER(C.c_int32), C.c_void_p]),
     "mvb_s1_step_logits": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "mvb_s1_launch_count": (C.c_uint64, [C.c_void_p]),
+    "mvb_s2_workspace_bytes": (C.c_size_t, [C.POINTER(S2Config)]),
+    "mvb_s2_create": (C.c_int, [C.POINTER(S2Config), C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.c_void_p,
+                                C.POINTER(C.c_void_p)]),
+    "mvb_s2_destroy": (C.c_int, [C.c_void_p]),
+    "mvb_s2_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_void_p,
+                                 C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mvb_linear": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_float,
                              C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
 }

@@ -178,3 +178,78 @@ def synthetic_speaker(seed: int = 11, dim: int = 256) -> torch.Tensor:
 
 def dims_as_dict(d: Stage1Dims) -> dict:
     return asdict(d)
+
+
+# ------------------------------------------------------------------------------------------------ stage 2
+@dataclass
+class Stage2Dims:
+    """Shape of the non-causal codebook-expansion model (fam/llm/model.py:26-46 GPTConfig, causal=False).
+    The real values live in second_stage.pt["model_args"] (not available offline); these defaults give the
+    "~10 Mn parameters" of README.md:164 and are only used for synthetic checkpoints."""
+
+    n_layer: int = 6
+    n_head: int = 6
+    n_embd: int = 384
+    block_size: int = 1024
+    vocab_sizes: tuple = (1538, 1025)        # hierarchy 0: 1024 codes + pad 1024 + 512 text + EOT 1537; hierarchy 1: codes + pad
+    target_vocab_sizes: tuple = (1025,) * 6  # codebooks 2..7 (+ pad)
+    speaker_emb_dim: int = 256
+    rmsnorm_eps: float = 1e-5
+    swiglu_multiple_of: int = 256
+
+    @property
+    def hidden(self) -> int:
+        h = int(2 * 4 * self.n_embd / 3)    # fam/llm/layers/layers.py:51-52
+        m = self.swiglu_multiple_of
+        return m * ((h + m - 1) // m)
+
+
+S2_FULL = Stage2Dims()
+S2_TINY = Stage2Dims(n_layer=2, n_head=2, n_embd=128, block_size=256)
+
+
+def stage2_model_args(d: Stage2Dims) -> dict:
+    return dict(n_layer=d.n_layer, n_head=d.n_head, n_embd=d.n_embd, block_size=d.block_size, bias=False,
+                vocab_sizes=list(d.vocab_sizes), target_vocab_sizes=list(d.target_vocab_sizes), causal=False,
+                norm_type="rmsnorm", rmsnorm_eps=d.rmsnorm_eps, nonlinearity_type="swiglu",
+                swiglu_multiple_of=d.swiglu_multiple_of, attn_kernel_type="torch_attn", spk_emb_on_text=True, dropout=0.0)
+
+
+def stage2_state_dict(d: Stage2Dims, seed: int = 1) -> Dict[str, torch.Tensor]:
+    """bf16 state dict with the slow-path GPT key names (fam/llm/model.py:118-146)."""
+    gen = torch.Generator().manual_seed(seed)
+    e, hd = d.n_embd, d.hidden
+    proj_std = 0.02 / math.sqrt(2 * d.n_layer)
+    gain = lambda: (1.0 + 0.1 * torch.empty(e).normal_(generator=gen)).to(torch.bfloat16)
+    sd: Dict[str, torch.Tensor] = {}
+    for i, v in enumerate(d.vocab_sizes):
+        sd[f"transformer.wtes.{i}.weight"] = _normal(gen, (v, e), 0.02)
+    sd["transformer.wpe.weight"] = _normal(gen, (d.block_size, e), 0.02)
+    for i in range(d.n_layer):
+        p = f"transformer.h.{i}."
+        sd[p + "ln_1.weight"] = gain()
+        sd[p + "ln_2.weight"] = gain()
+        sd[p + "attn.c_attn.weight"] = _normal(gen, (3 * e, e), 0.02)
+        sd[p + "attn.c_proj.weight"] = _normal(gen, (e, e), proj_std)
+        sd[p + "mlp.swiglu.w1.weight"] = _normal(gen, (hd, e), 0.02)
+        sd[p + "mlp.swiglu.w3.weight"] = _normal(gen, (hd, e), 0.02)
+        sd[p + "mlp.c_proj.weight"] = _normal(gen, (e, hd), proj_std)
+    sd["transformer.ln_f.weight"] = gain()
+    sd["speaker_cond_pos.weight"] = _normal(gen, (e, d.speaker_emb_dim), 0.02)
+    for i, v in enumerate(d.target_vocab_sizes):
+        sd[f"lm_heads.{i}.weight"] = _normal(gen, (v, e), 0.05)
+    return sd
+
+
+def stage2_checkpoint(d: Stage2Dims, seed: int = 1) -> dict:
+    tok = synthetic_tokenizer_meta(offset=1025)  # stage-2 text ids = bpe id + 1025, EOT = 1537 (model.py:15)
+    return dict(model=stage2_state_dict(d, seed), model_args=stage2_model_args(d), config=dict(causal=False),
+                meta=dict(tokenizer=tok, speaker_cond=True, speaker_emb_size=d.speaker_emb_dim), iter_num=0, best_val_loss=0.0)
+
+
+def synthetic_stage2_input(d: Stage2Dims, n_frames: int, n_text: int = 12, seed: int = 3):
+    """(text ids incl. EOT, cb0[n_frames], cb1[n_frames]) in stage-2 token space."""
+    gen = torch.Generator().manual_seed(seed)
+    text = torch.randint(1025, 1537, (n_text - 1,), generator=gen).tolist() + [1537]
+    cb = torch.randint(0, 1024, (2, n_frames), generator=gen)
+    return text, cb[0].tolist(), cb[1].tolist()
