@@ -101,24 +101,14 @@ def build_engine(device, utts, rank, world):
     d = synth.FULL
     cfg = ModelArgs.from_name("metavoice-1B")
     t0 = time.time()
+    arena = offsets = None
     if rank == 0:
         arena, offsets = pack_arena(synth.stage1_state_dict(d, 0), d.n_layer)
         arena = arena.to(device)
-    else:
-        arena, offsets = None, None
     bcast_ms = None
     if world > 1:
-        import torch.distributed as dist
-        meta = [offsets, None if arena is None else arena.numel()]
-        dist.broadcast_object_list(meta, src=0)
-        offsets, nbytes = meta
-        if arena is None:
-            arena = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        torch.cuda.synchronize(device); dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); dist.broadcast(arena, src=0); e1.record()   # the ONE collective of the path: NCCL over NVLink
-        torch.cuda.synchronize(device)
-        bcast_ms = e0.elapsed_time(e1)
+        from mvb200.distributed import broadcast_arena
+        arena, offsets, bcast_ms = broadcast_arena(arena, offsets, device)   # the ONE collective of the path: NCCL over NVLink
     model = Transformer(cfg, arena, offsets, device=device)
     model.setup_spk_cond_mask()
     model.setup_caches(2 * utts, cfg.block_size, kv_dtype="bf16")

@@ -50,6 +50,7 @@ struct PcMat {     // one weight matrix kind, static decomposition
 
 struct PcParams {
   int n_layer, D, F, V, H, S_max, R, n_utts, kv_fp32;
+  int pf_ahead;    // weight tiles prefetched into L2 ahead of the smem ring (0 = off)
   int a_sw32;      // weight tiles staged as 4 x [128 x 16] sub-tiles (32B swizzle) instead of one [128 x 64] (128B swizzle)
   float eps;
   PcMat m_qkv, m_o, m_w13, m_w2, m_head;
@@ -93,6 +94,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
       ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
+}
+
+// Pull a weight tile into L2 only (no smem, no barrier): HBM keeps streaming while the ring is full.
+__device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 // byte offset of the 16-byte chunk holding k..k+7 of activation row `row` inside the B operand
@@ -274,6 +280,40 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     if (lane == 0) {
       const uint64_t pol = ptx::policy_evict_first();
       uint32_t slot = 0, kv_ctr = 0;
+      // Flat view of this CTA's weight-tile schedule (layer-major: qkv, wo, w1|w3, w2; then the head), used by the
+      // L2 prefetch cursor that runs `pf_ahead` tiles in front of the smem ring.
+      const int nk_q = s_qkv.kb1 - s_qkv.kb0, nk_o = s_o.kb1 - s_o.kb0, nk_f = s_w13.kb1 - s_w13.kb0,
+                nk_2 = s_w2.kb1 - s_w2.kb0, nk_h = s_head.kb1 - s_head.kb0;
+      const int c_q = s_qkv.nt * nk_q, c_o = s_o.nt * nk_o, c_f = s_w13.nt * nk_f, c_2 = s_w2.nt * nk_2;
+      const int per_layer = c_q + c_o + c_f + c_2;
+      const int total_tiles = p.n_layer * per_layer + s_head.nt * nk_h;
+      auto prefetch_flat = [&](int n) {
+        if (n >= total_tiles) return;
+        const CUtensorMap* tm;
+        const PcSlice* sl;
+        int nk, layer = 0, m;
+        if (n >= p.n_layer * per_layer) {
+          m = n - p.n_layer * per_layer; tm = &tm_head; sl = &s_head; nk = nk_h;
+        } else {
+          layer = n / per_layer;
+          m = n - layer * per_layer;
+          if (m < c_q) { tm = &tm_qkv; sl = &s_qkv; nk = nk_q; }
+          else if (m < c_q + c_o) { m -= c_q; tm = &tm_o; sl = &s_o; nk = nk_o; }
+          else if (m < c_q + c_o + c_f) { m -= c_q + c_o; tm = &tm_w1; sl = &s_w13; nk = nk_f; }
+          else { m -= c_q + c_o + c_f; tm = &tm_w2; sl = &s_w2; nk = nk_2; }
+        }
+        const int ti = m / nk, kb = sl->kb0 + (m - ti * nk);
+        int t = sl->t0 + ti * sl->G;
+        if (sl == &s_w13 && t >= T1) { t -= T1; tm = &tm_w3; }
+        if (p.a_sw32) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_prefetch_3d(tm, kb * 64 + 16 * j, t * 128, layer);
+        } else {
+          tma_prefetch_3d(tm, kb * 64, t * 128, layer);
+        }
+      };
+      int issued = 0;
+      for (int n = 0; n < p.pf_ahead; ++n) prefetch_flat(n);
       auto gemm_tiles = [&](const CUtensorMap* tmA, const CUtensorMap* tmB2, int split_t, const PcSlice& sl, int layer) {
         for (int i = 0; i < sl.nt; ++i) {
           const int t = sl.t0 + i * sl.G;
@@ -282,6 +322,8 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           for (int kb = sl.kb0; kb < sl.kb1; ++kb) {
             const uint32_t s = slot % STAGES, ph = (slot / STAGES) & 1u;
             ++slot;
+            if (p.pf_ahead > 0) prefetch_flat(issued + p.pf_ahead);
+            ++issued;
             ptx::mbar_wait(ptx::smem_u32(b_empty + s), ph ^ 1u);
             const uint32_t full = ptx::smem_u32(b_full + s);
             ptx::mbar_arrive_expect_tx(full, PC_STAGE_BYTES);
