@@ -312,8 +312,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           tma_prefetch_3d(tm, kb * 64, t * 128, layer);
         }
       };
-      int issued = 0;
-      for (int n = 0; n < p.pf_ahead; ++n) prefetch_flat(n);
+      int issued = 0, pf_next = 0;   // prefetch only while the ring is full: idle producer time -> HBM keeps streaming into L2
       auto gemm_tiles = [&](const CUtensorMap* tmA, const CUtensorMap* tmB2, int split_t, const PcSlice& sl, int layer) {
         for (int i = 0; i < sl.nt; ++i) {
           const int t = sl.t0 + i * sl.G;
@@ -322,9 +321,18 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           for (int kb = sl.kb0; kb < sl.kb1; ++kb) {
             const uint32_t s = slot % STAGES, ph = (slot / STAGES) & 1u;
             ++slot;
-            if (p.pf_ahead > 0) prefetch_flat(issued + p.pf_ahead);
+            {
+              const uint32_t eb = ptx::smem_u32(b_empty + s);
+              if (!ptx::mbar_try_wait(eb, ph ^ 1u)) {
+                const long long t0 = clock64();
+                if (pf_next <= issued) pf_next = issued + 1;          // never prefetch a tile that is about to be loaded
+                while (!ptx::mbar_try_wait(eb, ph ^ 1u)) {
+                  if (pf_next < issued + 1 + p.pf_ahead && pf_next < total_tiles) prefetch_flat(pf_next++);
+                  else if (clock64() - t0 > 4000000000ll) __trap();
+                }
+              }
+            }
             ++issued;
-            ptx::mbar_wait(ptx::smem_u32(b_empty + s), ph ^ 1u);
             const uint32_t full = ptx::smem_u32(b_full + s);
             ptx::mbar_arrive_expect_tx(full, PC_STAGE_BYTES);
             const uint32_t dst = ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES);

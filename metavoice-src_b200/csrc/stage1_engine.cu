@@ -151,7 +151,7 @@ struct mvb_s1 {
   bool pc_ok = false;
   bool trace = false;
   bool a_sw32 = false;
-  int pf_ahead = 16;
+  int pf_ahead = 0;
   CUtensorMap tm3[6];                                 // 3-D (k, row, layer) maps: wqkv, wo, w1, w3, w2, head
   PcMat pm[5];
   size_t layer_stride_elems = 0;
