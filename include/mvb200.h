@@ -179,6 +179,35 @@ int mvb_s2_forward(mvb_s2* h, int32_t batch, const int32_t* d_idx, const float* 
                    int32_t top_k, const float* d_noise, uint64_t seed, int32_t* d_tokens, float* d_logits_out,
                    void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Vocoder, EnCodec-24 kHz decode path: RVQ decode (the diffusion condition `decode_latent`) and the SEANet decoder
+ * (causal conv stack + 2-layer LSTM), i.e. what mbd.tokens_to_wav (fam/llm/decoders.py:85, audiocraft 1.2.0 ->
+ * transformers EncodecModel.decode) evaluates first.  The multi-band diffusion UNets themselves are NOT implemented
+ * (their source/weights are unavailable: parity unpinned).  fp32 arena, weight norm folded. */
+typedef struct mvb_voc_config {
+  int32_t n_q;          /* 8 codebooks at 6 kbps */
+  int32_t hidden;       /* codebook / latent dim 128 */
+  int32_t n_filters;    /* 32 */
+  int32_t n_ratios;     /* 4 */
+  int32_t ratios[8];    /* 8, 5, 4, 2 */
+  int32_t kernel, res_kernel, last_kernel; /* 7, 3, 7 */
+  int32_t compress;     /* 2 */
+  int32_t max_frames;   /* workspace capacity in 75 Hz frames */
+} mvb_voc_config;
+typedef struct mvb_voc mvb_voc;
+
+size_t mvb_voc_workspace_bytes(const mvb_voc_config* cfg);
+/* offsets (host), fp32 tensors: codebooks[n_q] [1024,hidden] | conv_in {w[512,hidden,7], b} | lstm layer 0
+ * {w_ih, w_hh, b_ih+b_hh} | lstm layer 1 {..} | per ratio: up {w[Cin,Cout,2r], b}, res.block1 {w,b}, res.block3 {w,b},
+ * res.shortcut {w,b} | conv_out {w[1,32,7], b}. */
+int mvb_voc_create(const mvb_voc_config* cfg, const void* d_arena, size_t arena_bytes, const uint64_t* offsets,
+                   void* d_workspace, mvb_voc** out);
+int mvb_voc_destroy(mvb_voc* h);
+/* d_codes int32 [n_q, T] -> d_latent fp32 [hidden, T]  (EncodecResidualVectorQuantizer.decode) */
+int mvb_voc_decode_latent(mvb_voc* h, const int32_t* d_codes, int32_t T, float* d_latent, void* stream);
+/* d_codes int32 [n_q, T] -> d_wav fp32 [T * prod(ratios)]  (EncodecModel.decode, one chunk, 24 kHz) */
+int mvb_voc_decode(mvb_voc* h, const int32_t* d_codes, int32_t T, float* d_wav, void* stream);
+
 #define MVB_OK 0
 #define MVB_ERR_CUDA 1
 #define MVB_ERR_ARG 2

@@ -31,6 +31,12 @@ class S2Config(C.Structure):
                 ("vocab_out", C.c_int32 * 8), ("spk_dim", C.c_int32), ("norm_eps", C.c_float), ("max_batch", C.c_int32)]
 
 
+class VocConfig(C.Structure):
+    _fields_ = [("n_q", C.c_int32), ("hidden", C.c_int32), ("n_filters", C.c_int32), ("n_ratios", C.c_int32),
+                ("ratios", C.c_int32 * 8), ("kernel", C.c_int32), ("res_kernel", C.c_int32), ("last_kernel", C.c_int32),
+                ("compress", C.c_int32), ("max_frames", C.c_int32)]
+
+
 # name -> (restype, argtypes); also the list the symbol-export test checks against include/mvb200.h
 SIGNATURES = {
     "mvb_abi_version": (C.c_int, []),
@@ -60,6 +66,12 @@ SIGNATURES = {
     "mvb_s2_destroy": (C.c_int, [C.c_void_p]),
     "mvb_s2_forward": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_void_p,
                                  C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mvb_voc_workspace_bytes": (C.c_size_t, [C.POINTER(VocConfig)]),
+    "mvb_voc_create": (C.c_int, [C.POINTER(VocConfig), C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.c_void_p,
+                                 C.POINTER(C.c_void_p)]),
+    "mvb_voc_destroy": (C.c_int, [C.c_void_p]),
+    "mvb_voc_decode_latent": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mvb_voc_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "mvb_linear": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_float,
                              C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
 }

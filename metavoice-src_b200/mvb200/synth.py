@@ -253,3 +253,17 @@ def synthetic_stage2_input(d: Stage2Dims, n_frames: int, n_text: int = 12, seed:
     text = torch.randint(1025, 1537, (n_text - 1,), generator=gen).tolist() + [1537]
     cb = torch.randint(0, 1024, (2, n_frames), generator=gen)
     return text, cb[0].tolist(), cb[1].tolist()
+
+
+# ------------------------------------------------------------------------------------------------ codec
+def encodec_model_and_state_dict(seed: int = 0):
+    """Random-init EnCodec 24 kHz in the layout of the ``facebook/encodec_24khz`` checkpoint that audiocraft's
+    ``MultiBandDiffusion.get_mbd_24khz`` loads (fam/llm/decoders.py:13) through ``transformers.EncodecModel``.
+    Returns (module, state_dict); the module is only used by tests as the reference implementation."""
+    from transformers import EncodecConfig, EncodecModel
+    torch.manual_seed(seed)
+    m = EncodecModel(EncodecConfig()).eval()
+    with torch.no_grad():
+        for q in m.quantizer.layers:           # codebooks are zero-initialised buffers: give them content
+            q.codebook.embed.normal_(0.0, 1.0)
+    return m, {k: v.detach().clone() for k, v in m.state_dict().items()}

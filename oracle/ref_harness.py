@@ -30,7 +30,11 @@ def _import_reference():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
-    sys.modules.setdefault("librosa", types.ModuleType("librosa"))
+    if "librosa" not in sys.modules:
+        import importlib.machinery
+        stub = types.ModuleType("librosa")
+        stub.__spec__ = importlib.machinery.ModuleSpec("librosa", None)   # keep importlib.util.find_spec() callers happy
+        sys.modules["librosa"] = stub
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
