@@ -1,0 +1,116 @@
+"""Host-side mirror of the façade ``fam/llm/fast_inference.py::TTS`` over libmvb200.
+
+Same constructor keywords and the same ``synthesise(text, spk_ref_path, top_p, guidance_scale, temperature) -> path``
+contract (fast_inference.py:41-50, 111-119, 195).  Differences, all stated where they occur:
+  * checkpoints are read from a local directory (the reference calls ``snapshot_download``, :71; no network here);
+  * the speaker vector must already exist (``.pt`` tensor / ``.npy``) -- the LSTM speaker encoder runs once per
+    speaker and is disk-cached by the reference (inference.py:419-435); it is outside the hot path;
+  * the vocoder stage is the EnCodec decoder; the multi-band-diffusion refinement and the DeepFilterNet enhancer
+    (decoders.py:85, fast_inference.py:158-163) are not implemented (unpinned third-party code);
+  * the wav is written as plain PCM16 (the reference's ``audio_write`` also loudness-normalises, decoders.py:40-47; N2).
+"""
+from __future__ import annotations
+
+import os
+import re
+import struct
+import time
+import uuid
+from datetime import datetime
+from pathlib import Path
+from typing import Literal, Optional
+
+import numpy as np
+import torch
+
+from .fast_inference_utils import build_model, main
+from .second_stage import SecondStage, flattened_interleaved_decode
+from .tokenise import TrainedBPETokeniser
+from .vocoder import EncodecDecodeEngine
+
+_UNICODE = {8175: "'", 8189: "'", 8190: "'", 8208: "-", 8209: "-", 8210: "-", 8211: "-", 8212: "-", 8213: "-", 8214: "||",
+            8216: "'", 8217: "'", 8218: ",", 8219: "`", 8220: '"', 8221: '"', 8222: ",,", 8223: '"', 8228: ".", 8229: "..",
+            8230: "...", 8242: "'", 8243: '"', 8245: "'", 8246: '"', 180: "'", 2122: "TM"}
+
+
+def normalize_text(text: str) -> str:
+    """fam/llm/utils.py:12-52: map typographic punctuation, reject code points >= 256, collapse whitespace."""
+    text = text.translate(_UNICODE)
+    bad = {c for c in text if ord(c) >= 256}
+    if bad:
+        raise ValueError(f"Non-supported character found: {[(c, ord(c)) for c in bad]}")
+    text = text.replace("\t", " ").replace("\n", " ").replace("\r", " ").replace("*", " ").strip()
+    return re.sub(r"\s\s+", " ", text)
+
+
+def write_wav_pcm16(path: str, wav: np.ndarray, sample_rate: int) -> None:
+    pcm = (np.clip(wav, -1.0, 1.0) * 32767.0).astype("<i2").tobytes()
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + len(pcm)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 1, sample_rate,
+                                                                                       sample_rate * 2, 2, 16))
+        f.write(b"data" + struct.pack("<I", len(pcm)) + pcm)
+
+
+def load_speaker_embedding(path: str) -> torch.Tensor:
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"File {path} not found!")      # inference.py:420-421
+    if path.endswith(".npy"):
+        e = torch.from_numpy(np.load(path))
+    elif path.endswith(".pt"):
+        e = torch.load(path, map_location="cpu")
+    else:
+        raise NotImplementedError("speaker reference must be a precomputed embedding (.pt / .npy): the speaker encoder "
+                                  "is outside the accelerated path (SURVEY.md row N3)")
+    return e.reshape(1, -1).float()
+
+
+class TTS:
+    END_OF_AUDIO_TOKEN = 1024
+
+    def __init__(self, model_name: str = "metavoiceio/metavoice-1B-v0.1", *, seed: int = 1337, output_dir: str = "outputs",
+                 quantisation_mode: Optional[Literal["int4", "int8"]] = None, first_stage_path: Optional[str] = None,
+                 telemetry_origin: Optional[str] = None, encodec_state_dict=None, device: str = "cuda"):
+        self._device = device
+        self._model_dir = model_name
+        if not os.path.isdir(model_name):
+            raise FileNotFoundError(f"{model_name}: pass a local snapshot directory holding first_stage.pt / second_stage.pt "
+                                    "(there is no network access for snapshot_download)")
+        self.output_dir = output_dir
+        os.makedirs(self.output_dir, exist_ok=True)
+        self._first_stage_ckpt = first_stage_path or f"{self._model_dir}/first_stage.pt"
+        torch.manual_seed(seed)                                                        # inference.py:69-70
+        ck2 = torch.load(f"{self._model_dir}/second_stage.pt", map_location="cpu", weights_only=False)
+        tok2 = TrainedBPETokeniser(**ck2["meta"]["tokenizer"])
+        self.llm_second_stage = SecondStage(ck2, device=device, tokenizer=tok2)
+        if encodec_state_dict is None:
+            encodec_state_dict = torch.load(f"{self._model_dir}/encodec_24khz.pt", map_location="cpu", weights_only=False)
+        self.codec = EncodecDecodeEngine(encodec_state_dict, device=device)
+        self.precision = torch.bfloat16
+        self.model, self.tokenizer, self.smodel, self.model_size = build_model(
+            precision=self.precision, checkpoint_path=Path(self._first_stage_ckpt),
+            spk_emb_ckpt_path=Path(f"{self._model_dir}/speaker_encoder.pt"), device=device, compile=True,
+            compile_prefill=True, quantisation_mode=quantisation_mode)
+        self._seed = seed
+
+    def synthesise(self, text: str, spk_ref_path: str, top_p=0.95, guidance_scale=3.0, temperature=1.0) -> str:
+        text = normalize_text(text)
+        spk_emb = load_speaker_embedding(spk_ref_path)
+        start = time.time()
+        tokens = main(model=self.model, tokenizer=self.tokenizer, model_size=self.model_size, prompt=text, spk_emb=spk_emb,
+                      top_p=top_p, guidance_scale=guidance_scale, temperature=temperature, device=self._device)
+        _, extracted = flattened_interleaved_decode(tokens, self.END_OF_AUDIO_TOKEN)
+        codes = self.llm_second_stage.non_causal_sample(
+            texts=[text], encodec_tokens=[torch.tensor(extracted, dtype=torch.int32).unsqueeze(0)],
+            speaker_embs=spk_emb.unsqueeze(0), batch_size=1, top_k=200, temperature=1.0)[0]
+        wav = self.codec.decode(codes)
+        if wav.shape[-1] < 9600:
+            raise Exception("wav predicted is shorter than 400ms!")                    # decoders.py:88-91
+        name = f"synth_{datetime.now().strftime('%y-%m-%d--%H-%M-%S')}_{text.replace(' ', '_')[:25]}_{uuid.uuid4()}"
+        path = str(Path(self.output_dir).resolve() / name) + ".wav"
+        write_wav_pcm16(path, wav.cpu().numpy(), 24000)
+        print(f"\nSaved audio to {path}")
+        dt = time.time() - start
+        dur = wav.shape[-1] / 24000.0
+        print(f"\nTotal time to synth (s): {dt}")
+        print(f"Real-time factor: {dt / dur:.2f}")
+        return path
