@@ -22,7 +22,7 @@
 
 namespace mvb {
 
-constexpr int PC_THREADS = 192;      // producer warp + MMA warp + 4 compute warps
+constexpr int PC_THREADS = 224;      // producer warp + MMA warp + 4 compute warps + second producer warp
 constexpr int PC_STAGE_BYTES = 16384;
 constexpr int PC_RPAD = 16;          // rows of the fp32 activation buffers (8 utterances x 2 CFG rows)
 constexpr int PC_BKB_MAX = 12;       // k-blocks of B one CTA may own in a phase
@@ -50,6 +50,9 @@ struct PcMat {     // one weight matrix kind, static decomposition
 
 struct PcParams {
   int n_layer, D, F, V, H, S_max, R, n_utts, kv_fp32;
+  int n_prod;      // TMA producer threads (1 or 2): one issuing thread tops out at ~64 GB/s per SM (tools/micro/tma_bench)
+  int spin;        // 1: hot hand-off loops spin on mbarrier.test_wait instead of try_wait
+  int dbg;         // timing experiments only (wrong results): 1 = one UMMA per tile instead of four, 2 = no UMMA
   int pf_ahead;    // weight tiles prefetched into L2 ahead of the smem ring (0 = off)
   int a_sw32;      // weight tiles staged as 4 x [128 x 16] sub-tiles (32B swizzle) instead of one [128 x 64] (128B swizzle)
   float eps;
@@ -275,9 +278,12 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
                 s_w2 = pc_slice(p.m_w2, cta), s_head = pc_slice(p.m_head, cta);
   const int T1 = p.m_w13.T >> 1;  // w1 tiles; tiles >= T1 belong to w3
 
-  if (warp == 0) {
-    // =================================== PRODUCER ===================================================
-    if (lane == 0) {
+  if (warp == 0 || warp == 6) {
+    // =================================== PRODUCER(S) ================================================
+    // Weight tile n of the flat schedule is issued by producer (n % n_prod); producer 0 also feeds the KV slots.
+    const int pid = warp == 0 ? 0 : 1;
+    const int NPROD = p.n_prod;
+    if (lane == 0 && pid < NPROD) {
       const uint64_t pol = ptx::policy_evict_first();
       uint32_t slot = 0, kv_ctr = 0;
       // Flat view of this CTA's weight-tile schedule (layer-major: qkv, wo, w1|w3, w2; then the head), used by the
@@ -321,14 +327,17 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           for (int kb = sl.kb0; kb < sl.kb1; ++kb) {
             const uint32_t s = slot % STAGES, ph = (slot / STAGES) & 1u;
             ++slot;
+            if (NPROD > 1 && (issued % NPROD) != pid) { ++issued; continue; }   // the other producer's tile
             {
               const uint32_t eb = ptx::smem_u32(b_empty + s);
-              if (!ptx::mbar_try_wait(eb, ph ^ 1u)) {
+              if (!ptx::mbar_test_wait(eb, ph ^ 1u)) {
                 const long long t0 = clock64();
-                if (pf_next <= issued) pf_next = issued + 1;          // never prefetch a tile that is about to be loaded
-                while (!ptx::mbar_try_wait(eb, ph ^ 1u)) {
-                  if (pf_next < issued + 1 + p.pf_ahead && pf_next < total_tiles) prefetch_flat(pf_next++);
-                  else if (clock64() - t0 > 4000000000ll) __trap();
+                if (pf_next <= issued) pf_next = issued + NPROD;      // never prefetch a tile that is about to be loaded
+                // the ring is full: spend the producer's idle time pulling upcoming tiles into L2 (non-blocking probe)
+                while (!ptx::mbar_test_wait(eb, ph ^ 1u)) {
+                  if (pf_next < issued + 1 + p.pf_ahead && pf_next < total_tiles) { prefetch_flat(pf_next); pf_next += NPROD; }
+                  else if (p.spin) { if (clock64() - t0 > 4000000000ll) __trap(); }
+                  else if (!ptx::mbar_try_wait(eb, ph ^ 1u) && clock64() - t0 > 4000000000ll) __trap();
                 }
               }
             }
@@ -372,16 +381,18 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       for (int l = 0; l < p.n_layer; ++l) {
         if (l == 0) {
           gemm_tiles(&tm_qkv, &tm_qkv, 1 << 30, s_qkv, 0);   // weights first: they need nothing from the previous kernel
-          ptx::mbar_wait(ptx::smem_u32(tab_ready), 0);        // tile table built (after the PDL wait) by the compute warps
-          kv_units(0, 0, 1 << 30);
-        } else {
+          if (pid == 0) {
+            ptx::mbar_wait(ptx::smem_u32(tab_ready), 0);      // tile table built (after the PDL wait) by the compute warps
+            kv_units(0, 0, 1 << 30);
+          }
+        } else if (pid == 0) {
           kv_units(l, PC_NKV, 1 << 30);                       // (units beyond the prefetched ones)
         }
         gemm_tiles(&tm_o, &tm_o, 1 << 30, s_o, l);
         gemm_tiles(&tm_w1, &tm_w3, T1, s_w13, l);
         gemm_tiles(&tm_w2, &tm_w2, 1 << 30, s_w2, l);
         if (l + 1 < p.n_layer) {
-          kv_units(l + 1, 0, PC_NKV);                         // next layer's first KV tiles ride ahead of its QKV GEMM
+          if (pid == 0) kv_units(l + 1, 0, PC_NKV);           // next layer's first KV tiles ride ahead of its QKV GEMM
           gemm_tiles(&tm_qkv, &tm_qkv, 1 << 30, s_qkv, l + 1);
         }
       }
@@ -405,7 +416,8 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           for (int kb = sl.kb0; kb < sl.kb1; ++kb) {
             const uint32_t s = slot % STAGES, ph = (slot / STAGES) & 1u;
             ++slot;
-            ptx::mbar_wait(ptx::smem_u32(b_full + s), ph);
+            if (p.spin) ptx::mbar_spin(ptx::smem_u32(b_full + s), ph);
+            else ptx::mbar_wait(ptx::smem_u32(b_full + s), ph);
             ptx::tc_fence_after();
             const uint32_t a_addr = ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES);
             const uint64_t ad = ptx::umma_desc_k_sw128(a_addr);
@@ -414,10 +426,12 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 ptx::umma_bf16(dcol, ptx::umma_desc_k_sw32(a_addr + 4096 * k), bd + 2 * k, idesc, (uint32_t)((kb != sl.kb0) || k != 0));
-            } else {
+            } else if (p.dbg == 0) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 ptx::umma_bf16(dcol, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb != sl.kb0) || k != 0));
+            } else if (p.dbg == 1) {
+              ptx::umma_bf16(dcol, ad, bd, idesc, (uint32_t)(kb != sl.kb0));
             }
             ptx::umma_commit(ptx::smem_u32(b_empty + s));
           }

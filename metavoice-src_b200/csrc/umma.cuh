@@ -33,6 +33,26 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// Non-blocking probe (try_wait may suspend the thread for a system-dependent time; test_wait returns at once).
+__device__ __forceinline__ uint32_t mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Spin on the non-blocking probe (for the hot producer / MMA hand-off loops).
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
+  if (mbar_test_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_test_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
