@@ -430,10 +430,11 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 ptx::umma_bf16(dcol, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb != sl.kb0) || k != 0));
-            } else if (p.dbg == 1) {
+            } else if (p.dbg == 1 || p.dbg == 4) {
               ptx::umma_bf16(dcol, ad, bd, idesc, (uint32_t)(kb != sl.kb0));
             }
-            ptx::umma_commit(ptx::smem_u32(b_empty + s));
+            if (p.dbg == 3) ptx::mbar_arrive(ptx::smem_u32(b_empty + s));   // timing experiment: plain arrive instead of tcgen05.commit
+            else ptx::umma_commit(ptx::smem_u32(b_empty + s));
           }
           ptx::umma_commit(ptx::smem_u32(acc_full + ab));
           ++tile_ctr;
