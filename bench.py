@@ -272,6 +272,9 @@ def main():
         import torch.distributed as dist
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     ms_max, e2e_ms_max = [float(x) for x in times.cpu()]
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     total_toks = toks * world
@@ -300,7 +303,7 @@ def main():
         "init": {"build_s": round(build_s, 2), "nccl_broadcast_ms": bcast_ms},
         "pipeline": pipe,
     }
-    if not a.skip_cpu_baseline:
+    if not a.skip_cpu_baseline and world == 1:   # reported at N=1 only (rank 0 would otherwise hold the other ranks' cores)
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line))
 
