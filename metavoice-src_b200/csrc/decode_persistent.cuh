@@ -35,7 +35,8 @@ template <int NB> struct PcCfg {
   static constexpr int STAGES = (NB == 16) ? 8 : 6;
   static constexpr int B_BYTES = PC_BKB_MAX * NB * 128;
   static constexpr int RH = NB / 2;                      // activation rows carried (hi rows; lo rows follow)
-  static constexpr int TMEM_COLS = (2 * NB < 32) ? 32 : 2 * NB;
+  static constexpr int TMEM_COLS = 256;   // 2 accumulators (2 NB columns) + 4 weight-tile A buffers of 32 columns (A-in-TMEM mode)
+  static constexpr int A_COL0 = 2 * NB;
   static constexpr size_t SMEM = 1024 + (size_t)STAGES * PC_STAGE_BYTES + B_BYTES + (size_t)PC_NKV * 2 * PC_STAGE_BYTES +
                                  (2 * STAGES + 1 + 4 + 2 * PC_NKV + 1) * 8 + 16 + (1024 + 8 + 8 + PC_RPAD + 256 + 64) * 4 +
                                  PC_MAX_TILES * 16 + (PC_RPAD + 4) * 4 + 64;
@@ -51,10 +52,8 @@ struct PcMat {     // one weight matrix kind, static decomposition
 struct PcParams {
   int n_layer, D, F, V, H, S_max, R, n_utts, kv_fp32;
   int n_prod;      // TMA producer threads (1 or 2): one issuing thread tops out at ~64 GB/s per SM (tools/micro/tma_bench)
-  int spin;        // 1: hot hand-off loops spin on mbarrier.test_wait instead of try_wait
-  int dbg;         // timing experiments only (wrong results): 1 = one UMMA per tile instead of four, 2 = no UMMA
+  int ts;          // 1: copy each weight tile smem -> TMEM (tcgen05.cp) and run the UMMAs with A in tensor memory
   int pf_ahead;    // weight tiles prefetched into L2 ahead of the smem ring (0 = off)
-  int a_sw32;      // weight tiles staged as 4 x [128 x 16] sub-tiles (32B swizzle) instead of one [128 x 64] (128B swizzle)
   float eps;
   PcMat m_qkv, m_o, m_w13, m_w2, m_head;
   const __nv_bfloat16* attn_norm;   // layer 0; layer l at + l * layer_stride
@@ -271,7 +270,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (no operand waterfall at the tcgen05 sites)
   pdl_launch_dependents();
 
   const PcSlice s_qkv = pc_slice(p.m_qkv, cta), s_o = pc_slice(p.m_o, cta), s_w13 = pc_slice(p.m_w13, cta),
@@ -281,9 +280,12 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   if (warp == 0 || warp == 6) {
     // =================================== PRODUCER(S) ================================================
     // Weight tile n of the flat schedule is issued by producer (n % n_prod); producer 0 also feeds the KV slots.
+    // The whole warp walks the schedule (warp-uniform control flow and operands); one elected lane issues the TMA /
+    // bulk-copy instructions.  Issuing them from a `lane == 0` branch makes the compiler wrap each UTMALDG in an
+    // ELECT + 4 x R2UR.BROADCAST + vote loop, which capped one producer at a tile per ~0.25 us.
     const int pid = warp == 0 ? 0 : 1;
     const int NPROD = p.n_prod;
-    if (lane == 0 && pid < NPROD) {
+    if (pid < NPROD) {
       const uint64_t pol = ptx::policy_evict_first();
       uint32_t slot = 0, kv_ctr = 0;
       // Flat view of this CTA's weight-tile schedule (layer-major: qkv, wo, w1|w3, w2; then the head), used by the
@@ -311,12 +313,8 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         const int ti = m / nk, kb = sl->kb0 + (m - ti * nk);
         int t = sl->t0 + ti * sl->G;
         if (sl == &s_w13 && t >= T1) { t -= T1; tm = &tm_w3; }
-        if (p.a_sw32) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) tma_prefetch_3d(tm, kb * 64 + 16 * j, t * 128, layer);
-        } else {
-          tma_prefetch_3d(tm, kb * 64, t * 128, layer);
-        }
+        if (ptx::elect_one()) tma_prefetch_3d(tm, kb * 64, t * 128, layer);
+        __syncwarp();
       };
       int issued = 0, pf_next = 0;   // prefetch only while the ring is full: idle producer time -> HBM keeps streaming into L2
       auto gemm_tiles = [&](const CUtensorMap* tmA, const CUtensorMap* tmB2, int split_t, const PcSlice& sl, int layer) {
@@ -328,29 +326,23 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             const uint32_t s = slot % STAGES, ph = (slot / STAGES) & 1u;
             ++slot;
             if (NPROD > 1 && (issued % NPROD) != pid) { ++issued; continue; }   // the other producer's tile
-            {
-              const uint32_t eb = ptx::smem_u32(b_empty + s);
-              if (!ptx::mbar_test_wait(eb, ph ^ 1u)) {
-                const long long t0 = clock64();
-                if (pf_next <= issued) pf_next = issued + NPROD;      // never prefetch a tile that is about to be loaded
-                // the ring is full: spend the producer's idle time pulling upcoming tiles into L2 (non-blocking probe)
-                while (!ptx::mbar_test_wait(eb, ph ^ 1u)) {
-                  if (pf_next < issued + 1 + p.pf_ahead && pf_next < total_tiles) { prefetch_flat(pf_next); pf_next += NPROD; }
-                  else if (p.spin) { if (clock64() - t0 > 4000000000ll) __trap(); }
-                  else if (!ptx::mbar_try_wait(eb, ph ^ 1u) && clock64() - t0 > 4000000000ll) __trap();
-                }
+            const uint32_t eb = ptx::smem_u32(b_empty + s);
+            if (p.pf_ahead > 0 && !ptx::mbar_test_wait(eb, ph ^ 1u)) {
+              // the ring is full: spend the idle time pulling upcoming tiles into L2 (non-blocking probe)
+              if (pf_next <= issued) pf_next = issued + NPROD;      // never prefetch a tile that is about to be loaded
+              while (pf_next < issued + 1 + p.pf_ahead && pf_next < total_tiles && !ptx::mbar_test_wait(eb, ph ^ 1u)) {
+                prefetch_flat(pf_next);
+                pf_next += NPROD;
               }
             }
+            ptx::mbar_wait(eb, ph ^ 1u);
             ++issued;
-            const uint32_t full = ptx::smem_u32(b_full + s);
-            ptx::mbar_arrive_expect_tx(full, PC_STAGE_BYTES);
-            const uint32_t dst = ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES);
-            if (p.a_sw32) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) tma_load_3d(dst + 4096 * j, tm, full, kb * 64 + 16 * j, tt * 128, layer, pol);
-            } else {
-              tma_load_3d(dst, tm, full, kb * 64, tt * 128, layer, pol);
+            if (ptx::elect_one()) {
+              const uint32_t full = ptx::smem_u32(b_full + s);
+              ptx::mbar_arrive_expect_tx(full, PC_STAGE_BYTES);
+              tma_load_3d(ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES), tm, full, kb * 64, tt * 128, layer, pol);
             }
+            __syncwarp();
           }
         }
       };
@@ -370,12 +362,15 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           const uint32_t ks = kv_ctr % PC_NKV, ph = (kv_ctr / PC_NKV) & 1u;
           ++kv_ctr;
           ptx::mbar_wait(ptx::smem_u32(kv_empty + ks), ph ^ 1u);
-          const uint32_t bytes = (uint32_t)npos * 128 * esz;
-          const uint32_t full = ptx::smem_u32(kv_full + ks);
-          ptx::mbar_arrive_expect_tx(full, 2 * bytes);
-          uint8_t* dst = kvbuf + (size_t)ks * 2 * PC_STAGE_BYTES;
-          bulk_load(ptx::smem_u32(dst), kbase + e.off, bytes, full);
-          bulk_load(ptx::smem_u32(dst + PC_STAGE_BYTES), vbase + e.off, bytes, full);
+          if (ptx::elect_one()) {
+            const uint32_t bytes = (uint32_t)npos * 128 * esz;
+            const uint32_t full = ptx::smem_u32(kv_full + ks);
+            ptx::mbar_arrive_expect_tx(full, 2 * bytes);
+            uint8_t* dst = kvbuf + (size_t)ks * 2 * PC_STAGE_BYTES;
+            bulk_load(ptx::smem_u32(dst), kbase + e.off, bytes, full);
+            bulk_load(ptx::smem_u32(dst + PC_STAGE_BYTES), vbase + e.off, bytes, full);
+          }
+          __syncwarp();
         }
       };
       for (int l = 0; l < p.n_layer; ++l) {
@@ -400,9 +395,13 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     }
   } else if (warp == 1) {
     // =================================== MMA ISSUER =================================================
-    if (lane == 0) {
+    // The WHOLE warp walks the schedule (waits, counters, descriptor arithmetic stay warp-uniform -> uniform
+    // registers) and one elected lane issues the tcgen05 instructions.  Issuing from a `lane == 0` branch makes the
+    // compiler wrap every UTCHMMA in an R2UR / ELECT / vote loop: 175 instead of 134 cycles per instruction
+    // (tools/micro/umma_bench.cu).
+    {
       const uint32_t idesc = ptx::umma_idesc_bf16(128, NB);
-      uint32_t slot = 0, tile_ctr = 0, bphase = 0;
+      uint32_t slot = 0, tile_ctr = 0, bphase = 0, a_ctr = 0;
       auto gemm_phase = [&](const PcSlice& sl) {
         if (sl.nt == 0) return;
         ptx::mbar_wait(ptx::smem_u32(b_ready), bphase & 1u);   // B operand of this phase staged
@@ -416,27 +415,33 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           for (int kb = sl.kb0; kb < sl.kb1; ++kb) {
             const uint32_t s = slot % STAGES, ph = (slot / STAGES) & 1u;
             ++slot;
-            if (p.spin) ptx::mbar_spin(ptx::smem_u32(b_full + s), ph);
-            else ptx::mbar_wait(ptx::smem_u32(b_full + s), ph);
+            ptx::mbar_wait(ptx::smem_u32(b_full + s), ph);
             ptx::tc_fence_after();
             const uint32_t a_addr = ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES);
             const uint64_t ad = ptx::umma_desc_k_sw128(a_addr);
             const uint64_t bd = ptx::umma_desc_k_sw128(ptx::smem_u32(Bop + (size_t)(kb - sl.kb0) * (NB * 128)));
-            if (p.a_sw32) {
+            const uint32_t first = (uint32_t)(kb != sl.kb0);
+            if (p.ts) {
+              // Experimental (MVB_PC_TS=1, parity-tested, not faster): copy the tile to tensor memory with tcgen05.cp,
+              // release the smem stage once the copy is done, run the UMMAs with A in TMEM.
+              const uint32_t abuf = tmem_base + Cfg::A_COL0 + (a_ctr & 3u) * 32;
+              ++a_ctr;
+              if (ptx::elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                ptx::umma_bf16(dcol, ptx::umma_desc_k_sw32(a_addr + 4096 * k), bd + 2 * k, idesc, (uint32_t)((kb != sl.kb0) || k != 0));
-            } else if (p.dbg == 0) {
+                for (int k = 0; k < 4; ++k) ptx::tmem_cp_128x256b(abuf + 8 * k, ad + 2 * k);
+                ptx::umma_commit(ptx::smem_u32(b_empty + s));
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                ptx::umma_bf16(dcol, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb != sl.kb0) || k != 0));
-            } else if (p.dbg == 1 || p.dbg == 4) {
-              ptx::umma_bf16(dcol, ad, bd, idesc, (uint32_t)(kb != sl.kb0));
+                for (int k = 0; k < 4; ++k) ptx::umma_bf16_ts(dcol, abuf + 8 * k, bd + 2 * k, idesc, first | (uint32_t)(k != 0));
+              }
+            } else if (ptx::elect_one()) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) ptx::umma_bf16(dcol, ad + 2 * k, bd + 2 * k, idesc, first | (uint32_t)(k != 0));
+              ptx::umma_commit(ptx::smem_u32(b_empty + s));
             }
-            if (p.dbg == 3) ptx::mbar_arrive(ptx::smem_u32(b_empty + s));   // timing experiment: plain arrive instead of tcgen05.commit
-            else ptx::umma_commit(ptx::smem_u32(b_empty + s));
+            __syncwarp();
           }
-          ptx::umma_commit(ptx::smem_u32(acc_full + ab));
+          if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(acc_full + ab));
+          __syncwarp();
           ++tile_ctr;
         }
       };

@@ -151,7 +151,7 @@ struct mvb_s1 {
   bool pc_ok = false;
   bool trace = false;
   bool a_sw32 = false;
-  int pf_ahead = 0;
+  int pf_ahead = 8;
   CUtensorMap tm3[6];                                 // 3-D (k, row, layer) maps: wqkv, wo, w1, w3, w2, head
   PcMat pm[5];
   size_t layer_stride_elems = 0;
@@ -286,7 +286,6 @@ extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size
   }
   if (const char* e = getenv("MVB_PATHC")) h->path_c = atoi(e) != 0;
   if (const char* e = getenv("MVB_PC_TRACE")) h->trace = atoi(e) != 0;
-  if (const char* e = getenv("MVB_A_SW32")) h->a_sw32 = atoi(e) != 0;
   if (const char* e = getenv("MVB_PF_AHEAD")) h->pf_ahead = atoi(e);
   {
     // persistent decode kernel: needs a uniform layer stride (true for arenas packed in checkpoint order)
@@ -515,12 +514,10 @@ static int launch_persistent(mvb_s1* h, cudaStream_t s, int n_utts) {
   const mvb_s1_config& c = h->cfg;
   PcParams p{};
   p.n_layer = c.n_layer; p.D = c.dim; p.F = c.intermediate; p.V = c.vocab; p.H = c.n_head; p.S_max = c.block_size;
-  p.a_sw32 = h->a_sw32 ? 1 : 0;
   p.pf_ahead = h->pf_ahead;
-  p.n_prod = getenv("MVB_PC_NPROD") ? atoi(getenv("MVB_PC_NPROD")) : 2;
-  if (p.n_prod < 1 || p.n_prod > 2) p.n_prod = 2;
-  p.spin = getenv("MVB_PC_SPIN") ? atoi(getenv("MVB_PC_SPIN")) : 0;
-  p.dbg = getenv("MVB_PC_DBG") ? atoi(getenv("MVB_PC_DBG")) : 0;
+  p.ts = getenv("MVB_PC_TS") ? atoi(getenv("MVB_PC_TS")) : 0;
+  p.n_prod = getenv("MVB_PC_NPROD") ? atoi(getenv("MVB_PC_NPROD")) : 1;
+  if (p.n_prod < 1 || p.n_prod > 2) p.n_prod = 1;
   p.R = 2 * n_utts; p.n_utts = n_utts; p.kv_fp32 = c.kv_dtype == MVB_KV_FP32; p.eps = c.norm_eps;
   p.m_qkv = h->pm[0]; p.m_o = h->pm[1]; p.m_w13 = h->pm[2]; p.m_w2 = h->pm[3]; p.m_head = h->pm[4];
   p.attn_norm = h->lw(0, 0); p.ffn_norm = h->lw(0, 3); p.out_norm = h->w(3);
