@@ -110,28 +110,31 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (see decode_persistent.cuh)
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
+    // ===== TMA producer: the whole warp walks the loop (uniform operands), one elected lane issues =====
+    {
       const uint64_t pol_w = ptx::policy_evict_first();  // weights are streamed exactly once per pass
       for (int it = 0; it < n_it; ++it) {
         const int s = it % S;
         const uint32_t ph = (uint32_t)(it / S) & 1u;
         ptx::mbar_wait(ptx::smem_u32(bars + S + s), ph ^ 1u);
-        const uint32_t full = ptx::smem_u32(bars + s);
-        ptx::mbar_arrive_expect_tx(full, (uint32_t)stage_bytes);
-        uint8_t* st = smem + (size_t)s * stage_bytes;
-        const int kc = (kb0 + it) * 64;
-        ptx::tma_load_2d_hint(ptx::smem_u32(st), &tmA, full, kc, tile * 128, pol_w);
-        if (NA == 2) ptx::tma_load_2d_hint(ptx::smem_u32(st + GEMM_A_BYTES), &tmA3, full, kc, tile * 128, pol_w);
-        ptx::tma_load_2d(ptx::smem_u32(st + NA * GEMM_A_BYTES), &tmB, full, kc, 0);
+        if (ptx::elect_one()) {
+          const uint32_t full = ptx::smem_u32(bars + s);
+          ptx::mbar_arrive_expect_tx(full, (uint32_t)stage_bytes);
+          uint8_t* st = smem + (size_t)s * stage_bytes;
+          const int kc = (kb0 + it) * 64;
+          ptx::tma_load_2d_hint(ptx::smem_u32(st), &tmA, full, kc, tile * 128, pol_w);
+          if (NA == 2) ptx::tma_load_2d_hint(ptx::smem_u32(st + GEMM_A_BYTES), &tmA3, full, kc, tile * 128, pol_w);
+          ptx::tma_load_2d(ptx::smem_u32(st + NA * GEMM_A_BYTES), &tmB, full, kc, 0);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
+    // ===== MMA issuer: warp-uniform loop, one elected lane issues (a lane-0 branch costs ~40 cycles per UMMA) =====
+    {
       const uint32_t idesc = ptx::umma_idesc_bf16(128, p.NB);
       for (int it = 0; it < n_it; ++it) {
         const int s = it % S;
@@ -141,18 +144,22 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint8_t* st = smem + (size_t)s * stage_bytes;
         const uint64_t ad = ptx::umma_desc_k_sw128(ptx::smem_u32(st));
         const uint64_t bd = ptx::umma_desc_k_sw128(ptx::smem_u32(st + NA * GEMM_A_BYTES));
+        const uint64_t a3 = ptx::umma_desc_k_sw128(ptx::smem_u32(st + GEMM_A_BYTES));
+        if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)  // 4 x (K = 16) per 64-wide k-block: +32 B along K inside the swizzle atom
-          ptx::umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((it | k) != 0));
-        if (NA == 2) {
-          const uint64_t a3 = ptx::umma_desc_k_sw128(ptx::smem_u32(st + GEMM_A_BYTES));
+          for (int k = 0; k < 4; ++k)  // 4 x (K = 16) per 64-wide k-block: +32 B along K inside the swizzle atom
+            ptx::umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((it | k) != 0));
+          if (NA == 2) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16(tmem_base + (uint32_t)p.NB, a3 + 2 * k, bd + 2 * k, idesc, (uint32_t)((it | k) != 0));
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_bf16(tmem_base + (uint32_t)p.NB, a3 + 2 * k, bd + 2 * k, idesc, (uint32_t)((it | k) != 0));
+          }
+          ptx::umma_commit(ptx::smem_u32(bars + S + s));  // frees the smem stage when these MMAs retire
         }
-        ptx::umma_commit(ptx::smem_u32(bars + S + s));  // frees the smem stage when these MMAs retire
+        __syncwarp();
       }
-      ptx::umma_commit(ptx::smem_u32(bars + 2 * S));     // accumulator complete
+      if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(bars + 2 * S));     // accumulator complete
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> (split-K reduce) -> fused operator epilogue =====
