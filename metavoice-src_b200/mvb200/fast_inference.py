@@ -33,6 +33,9 @@ _UNICODE = {8175: "'", 8189: "'", 8190: "'", 8208: "-", 8209: "-", 8210: "-", 82
             8230: "...", 8242: "'", 8243: '"', 8245: "'", 8246: '"', 180: "'", 2122: "TM"}
 
 
+from .audio_out import audio_write_wav  # noqa: E402
+
+
 def normalize_text(text: str) -> str:
     """fam/llm/utils.py:12-52: map typographic punctuation, reject code points >= 256, collapse whitespace."""
     text = text.translate(_UNICODE)
@@ -106,8 +109,9 @@ class TTS:
         if wav.shape[-1] < 9600:
             raise Exception("wav predicted is shorter than 400ms!")                    # decoders.py:88-91
         name = f"synth_{datetime.now().strftime('%y-%m-%d--%H-%M-%S')}_{text.replace(' ', '_')[:25]}_{uuid.uuid4()}"
-        path = str(Path(self.output_dir).resolve() / name) + ".wav"
-        write_wav_pcm16(path, wav.cpu().numpy(), 24000)
+        # decoders.py:40-47: audio_write(strategy="loudness", loudness_compressor=True) -> <name>.wav
+        path = audio_write_wav(str(Path(self.output_dir).resolve() / name), wav.reshape(1, -1), 24000,
+                               strategy="loudness", loudness_compressor=True)
         print(f"\nSaved audio to {path}")
         dt = time.time() - start
         dur = wav.shape[-1] / 24000.0

@@ -159,15 +159,17 @@ def test_batched_mixed_lengths_equal_single_runs(tiny_sd):
     assert mismatches <= 2
 
 
-def test_persistent_kernel_batch_logits_match_single(tiny_sd):
-    """Same state, batch of 3 vs each utterance alone through the persistent kernel: logits agree to reduction-order
-    noise (fp32 KV) / bf16 rounding flips of the appended K,V (bf16 KV)."""
+@pytest.mark.parametrize("lens", [[5, 17, 9], [5, 17, 9, 12, 3, 20, 8]], ids=["batch3_n16", "batch7_n32"])
+def test_persistent_kernel_batch_logits_match_single(tiny_sd, lens):
+    """Same state, batch of 3 (16-column UMMA variant) / 7 (32-column variant) vs each utterance alone through the
+    persistent kernel: logits agree to reduction-order noise (fp32 KV) / bf16 rounding flips of the appended K,V
+    (bf16 KV)."""
     import ctypes as C
     from mvb200 import _lib
     d = synth.TINY
-    lens = [5, 17, 9]
+    n = len(lens)
     prompts = [synth.synthetic_prompt(T, seed=20 + i) for i, T in enumerate(lens)]
-    spks = [synth.synthetic_speaker(seed=30 + i) for i in range(3)]
+    spks = [synth.synthetic_speaker(seed=30 + i) for i in range(n)]
 
     def run(kv, n_slots, which):
         m = _mk(d, tiny_sd, kv, utts=n_slots)
@@ -185,8 +187,8 @@ def test_persistent_kernel_batch_logits_match_single(tiny_sd):
         return outs
 
     for kv, tol in (("fp32", 3e-5), ("bf16", 3e-4)):
-        batch = run(kv, 3, [0, 1, 2])
-        for i in range(3):
+        batch = run(kv, n, list(range(n)))
+        for i in range(n):
             single = run(kv, 1, [i])
             for step in range(3):
                 assert _rel(batch[step][2 * i:2 * i + 2], single[step]) < tol
