@@ -296,8 +296,8 @@ def main():
                      "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": round(achieved / peak, 4),
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture
-                     # (profiles/r1_ncu_persistent_summary.md, context length 52: algorithmic bytes there = 2.518e9)
-                     "traffic": 2504400000, "traffic_context_len": 52, "bytes_per_launch": int(step_bytes),
+                     # (profiles/r1_ncu_persistent_final_summary.md, context length 58: algorithmic bytes there = 2.500e9)
+                     "traffic": 2627800000, "traffic_context_len": 58, "bytes_per_launch": int(step_bytes),
                      "ms_per_launch": round(step_ms, 4), "context_len": L_mid},
         "clocks": clk.summary(),
         "init": {"build_s": round(build_s, 2), "nccl_broadcast_ms": bcast_ms},
