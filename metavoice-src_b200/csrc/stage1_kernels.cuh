@@ -552,7 +552,12 @@ __global__ void __launch_bounds__(SAMP_THREADS) k_sample(SampleP p, S1State st) 
           sid[i] = ib; sid[ixj] = ia;
         }
       }
-      __syncthreads();
+      // strides <= 32: a warp's 32 pair slots (and the second batch at +SAMP_THREADS) stay inside its own two
+      // 64-element blocks for all of j = 32 .. 1, so consecutive warp-local stages only need a warp barrier
+      // (27 block barriers instead of 78 for 4096 keys)
+      const int nj = (j > 1) ? (j >> 1) : k;   // stride of the next stage
+      if (j > 32 || nj > 32) __syncthreads();
+      else __syncwarp();
     }
   }
 
