@@ -28,7 +28,7 @@ for item in spec.split(","):
     parts = item.split(":")
     kind, n = parts[0], int(parts[1])
     os.environ["MVB_PF_AHEAD"] = parts[2] if len(parts) > 2 else "0"
-    os.environ["MVB_PC_NPROD"] = parts[3] if len(parts) > 3 else "2"
+    os.environ["MVB_PC_NPROD"] = parts[3] if len(parts) > 3 else "1"
     os.environ["MVB_PDL"] = "0" if kind.endswith("0") else "1"
     os.environ["MVB_DECODE_B_MIN"] = "1" if kind.startswith("B") else "9999"
     os.environ["MVB_PATHC"] = "1" if kind[0] in "CS" else "0"
