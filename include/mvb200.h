@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define MVB_ABI_VERSION 1
+#define MVB_ABI_VERSION 2
 
 /* KV-cache element type.  bf16 is what the reference stores (fast_model.py:97-102);
  * fp32 is the validation mode used for the <=1e-3 parity gate against the fp32 oracle. */
@@ -103,14 +103,17 @@ int mvb_s1_sample(mvb_s1* h, const float* d_logits, const mvb_sampling* p, const
  *   prompts      host int32, concatenated; prompt_lens[n_utts]
  *   spk_embs     host fp32 [n_utts, spk_dim]
  *   params       [n_utts]
- *   noise        host or NULL: fp32 [n_utts, max_new_tokens, vocab] Exp(1) draws in the reference's call order
+ *   noise        NULL, or fp32 [n_utts, max_new_tokens, vocab] Exp(1) draws in the reference's call order
+ *                (utils:61-65: one `q` per generated token).  noise_on_device == 0: HOST buffer, staged to the device
+ *                one burst of decode steps at a time; != 0: DEVICE buffer used in place (how the Python shim hands
+ *                over the draws it makes with torch's generator, so that torch.manual_seed reproduces the reference)
  *   forced       host or NULL: int32 [n_utts, max_new_tokens] teacher-forced feedback tokens (test hook)
  *   out_tokens   host int32 [n_utts, max_new_tokens]; out_lens[n_utts] = tokens produced (EOA included, utils:226)
  * Raises (returns MVB_ERR_PROMPT_TOO_LONG) when a prompt leaves no room: utils:203-204. */
 int mvb_s1_generate(mvb_s1* h, int32_t n_utts, const int32_t* prompts, const int32_t* prompt_lens,
                     const float* spk_embs, const mvb_sampling* params, int32_t max_new_tokens,
-                    const float* noise, const int32_t* forced, int32_t* out_tokens, int32_t* out_lens,
-                    void* stream);
+                    const float* noise, int32_t noise_on_device, const int32_t* forced, int32_t* out_tokens,
+                    int32_t* out_lens, void* stream);
 
 /* Same loop with inputs already resident: prompts/speakers must have been installed with
  * mvb_s1_set_speaker + mvb_s1_forward (prefill).  Runs `n_steps` decode steps for utterances
@@ -135,6 +138,14 @@ int mvb_s1_step_logits(mvb_s1* h, int32_t n_utts, float* d_logits, void* stream)
 
 /* Kernel launches issued by this handle since creation (bench.py "gpu_launches"). */
 uint64_t mvb_s1_launch_count(const mvb_s1* h);
+
+/* Test / debug hooks (not part of the drop-in surface; used by tests/ and tools/ only):
+ *   mvb_s1_fetch_sampled : the sampler's own draws for `utt` (they differ from the fed-back tokens of mvb_s1_fetch only
+ *                          under teacher forcing), host int32 [cap];
+ *   mvb_s1_trace_fetch   : per-CTA clock64 phase stamps of the last persistent-kernel step (MVB_PC_TRACE=1), host
+ *                          int64 [max_ctas, 512]; returns the number of CTAs copied. */
+int mvb_s1_fetch_sampled(mvb_s1* h, int32_t utt, int32_t* out_tokens, int32_t cap, void* stream);
+int mvb_s1_trace_fetch(mvb_s1* h, long long* out, int32_t max_ctas, void* stream);
 
 /* Tensor-core linear operator (tcgen05 + TMA weight streaming), the building block of the batched /
  * prefill path and of the stage-2 model: y[R, M] (+)= f(x)[R, K] . W[M, K]^T, W bf16 row-major [out, in]

@@ -51,8 +51,8 @@ static inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a
 
 struct WsLayout {
   size_t x, qkv, att, ffn, logits, spk, part_o, part_ml;
-  size_t slot_map, pos, row_tok, done, n_gen, gen_tokens, sampled, samp, noise, forced, ticket;
-  size_t stage_idx, stage_spk, stage_forced;
+  size_t slot_map, pos, row_tok, done, n_gen, gen_tokens, sampled, samp, noise, forced, ticket, budget, noise_base;
+  size_t stage_idx, stage_spk, stage_forced, stage_noise;
   // path B (tensor-core rows path): activations for up to RB_MAX rows
   size_t b_x, b_qkv, b_att, b_ffn, b_logits, b_last, b_B, b_rows, b_scratch, b_tickets, b_part_o, b_part_ml, b_att_tickets;
   // path C (persistent decode kernel)
@@ -62,6 +62,7 @@ struct WsLayout {
 
 constexpr int RB_MAX = 128;        // rows per tensor-core pass: 64-token prefill chunk x 2 CFG rows, or 64 utterances
 constexpr int PREFILL_CHUNK = 64;
+constexpr int GEN_BURST = 32;       // decode steps between two host polls of the done flags in mvb_s1_generate
 
 static WsLayout make_layout(const mvb_s1_config& c) {
   WsLayout L;
@@ -87,9 +88,12 @@ static WsLayout make_layout(const mvb_s1_config& c) {
   L.noise = take(U * sizeof(void*));
   L.forced = take(U * sizeof(void*));
   L.ticket = take(R * H * 4);
+  L.budget = take(U * 4);
+  L.noise_base = take(U * 4);
   L.stage_idx = take(U * 2 * (size_t)c.block_size * 4);
   L.stage_spk = take(U * (size_t)c.spk_dim * 4);
   L.stage_forced = take(U * (size_t)c.max_new * 4);
+  L.stage_noise = take(U * (size_t)GEN_BURST * V * 4);   // host-supplied Exp(1) draws are staged one burst at a time
   {
     const size_t RB = RB_MAX, NBM = 2 * RB_MAX;
     L.b_x = take(RB * D * 4);
@@ -152,6 +156,7 @@ struct mvb_s1 {
   bool trace = false;
   bool a_sw32 = false;
   int pf_ahead = 8;
+  int pc_ts = 0, pc_nprod = 1;                        // experiment switches, read once at create (MVB_PC_TS, MVB_PC_NPROD)
   CUtensorMap tm3[6];                                 // 3-D (k, row, layer) maps: wqkv, wo, w1, w3, w2, head
   PcMat pm[5];
   size_t layer_stride_elems = 0;
@@ -237,14 +242,18 @@ extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size
   CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   CK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
   if (major != 10) return fail(MVB_ERR_UNSUPPORTED, "libmvb200 is built for sm_100a only; device is sm_%d%d", major, minor);
-  mvb_s1* h = new mvb_s1();
+  struct Guard {   // frees the half-built handle on every early return below
+    mvb_s1* h;
+    ~Guard() { if (h) mvb_s1_destroy(h); }
+  } guard{new mvb_s1()};
+  mvb_s1* h = guard.h;
   h->cfg = *cfg;
   CK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dev));
   h->arena = reinterpret_cast<const char*>(d_arena);
   const int n_off = MVB_S1_GLOBAL_TENSORS + cfg->n_layer * MVB_S1_LAYER_TENSORS;
   h->off.assign(offsets, offsets + n_off);
   for (uint64_t o : h->off)
-    if (o % 16 || o >= arena_bytes) { delete h; return fail(MVB_ERR_ARG, "weight offset %llu not 16B-aligned or outside the arena", (unsigned long long)o); }
+    if (o % 16 || o >= arena_bytes) return fail(MVB_ERR_ARG, "weight offset %llu not 16B-aligned or outside the arena", (unsigned long long)o);
   h->kv = reinterpret_cast<char*>(d_kv);
   h->ws = reinterpret_cast<char*>(d_ws);
   h->L = make_layout(*cfg);
@@ -260,6 +269,8 @@ extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size
   s.noise = h->wsp<const float*>(h->L.noise);
   s.forced = h->wsp<const int*>(h->L.forced);
   s.attn_ticket = h->wsp<unsigned>(h->L.ticket);
+  s.budget = h->wsp<int>(h->L.budget);
+  s.noise_base = h->wsp<int>(h->L.noise_base);
   s.max_new = cfg->max_new;
   s.block_size = cfg->block_size;
   h->use_graph = getenv("MVB_NO_GRAPH") == nullptr;
@@ -282,11 +293,13 @@ extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size
       ok = ok && make_tmap_bf16(&h->tmW[l * 5 + 4], h->lw(l, 6), D, F, 128);
     }
     ok = ok && make_tmap_bf16(&h->tmW[(size_t)cfg->n_layer * 5], h->w(4), cfg->vocab, D, 128);
-    if (!ok) { delete h; return fail(MVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight matrix"); }
+    if (!ok) return fail(MVB_ERR_CUDA, "cuTensorMapEncodeTiled failed for a weight matrix");
   }
   if (const char* e = getenv("MVB_PATHC")) h->path_c = atoi(e) != 0;
   if (const char* e = getenv("MVB_PC_TRACE")) h->trace = atoi(e) != 0;
   if (const char* e = getenv("MVB_PF_AHEAD")) h->pf_ahead = atoi(e);
+  if (const char* e = getenv("MVB_PC_TS")) h->pc_ts = atoi(e);
+  if (const char* e = getenv("MVB_PC_NPROD")) h->pc_nprod = (atoi(e) == 2) ? 2 : 1;
   {
     // persistent decode kernel: needs a uniform layer stride (true for arenas packed in checkpoint order)
     const int D = cfg->dim, F = cfg->intermediate, V = cfg->vocab;
@@ -314,8 +327,15 @@ extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size
     ok = ok && (F % 128 == 0) && (D % 128 == 0);
     h->pc_ok = ok;
   }
+  // Opt-in shared-memory size is a per-device function attribute: set it for the device this handle lives on
+  // (a process may hold engines on several GPUs).
+  CK(cudaFuncSetAttribute(k_decode_persistent<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PcCfg<32>::SMEM));
+  CK(cudaFuncSetAttribute(k_decode_persistent<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PcCfg<16>::SMEM));
+  CK(cudaFuncSetAttribute(k_decode_persistent<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PcCfg<32>::SMEM));
+  CK(cudaFuncSetAttribute(k_decode_persistent<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PcCfg<16>::SMEM));
   CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
   CK(cudaMallocHost(&h->h_flags, sizeof(int) * 4 * 64));
+  guard.h = nullptr;
   *out = h;
   return MVB_OK;
 }
@@ -515,9 +535,8 @@ static int launch_persistent(mvb_s1* h, cudaStream_t s, int n_utts) {
   PcParams p{};
   p.n_layer = c.n_layer; p.D = c.dim; p.F = c.intermediate; p.V = c.vocab; p.H = c.n_head; p.S_max = c.block_size;
   p.pf_ahead = h->pf_ahead;
-  p.ts = getenv("MVB_PC_TS") ? atoi(getenv("MVB_PC_TS")) : 0;
-  p.n_prod = getenv("MVB_PC_NPROD") ? atoi(getenv("MVB_PC_NPROD")) : 1;
-  if (p.n_prod < 1 || p.n_prod > 2) p.n_prod = 1;
+  p.ts = h->pc_ts;
+  p.n_prod = h->pc_nprod;
   p.R = 2 * n_utts; p.n_utts = n_utts; p.kv_fp32 = c.kv_dtype == MVB_KV_FP32; p.eps = c.norm_eps;
   p.m_qkv = h->pm[0]; p.m_o = h->pm[1]; p.m_w13 = h->pm[2]; p.m_w2 = h->pm[3]; p.m_head = h->pm[4];
   p.attn_norm = h->lw(0, 0); p.ffn_norm = h->lw(0, 3); p.out_norm = h->w(3);
@@ -534,12 +553,6 @@ static int launch_persistent(mvb_s1* h, cudaStream_t s, int n_utts) {
   const bool fp = p.kv_fp32 != 0, wide = p.R > PcCfg<16>::RH;
 #define MVB_PC_LAUNCH(FP, NBV, IDX)                                                                                   \
   do {                                                                                                                \
-    static bool attr_set = false;                                                                                     \
-    if (!attr_set) {                                                                                                  \
-      CK(cudaFuncSetAttribute(k_decode_persistent<FP, NBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
-                              (int)PcCfg<NBV>::SMEM));                                                                \
-      attr_set = true;                                                                                                \
-    }                                                                                                                 \
     CK(launch_pdl(h->pdl, k_decode_persistent<FP, NBV>, dim3(h->n_sm), dim3(PC_THREADS), PcCfg<NBV>::SMEM, s,         \
                   h->tm3[0], h->tm3[1], h->tm3[2], h->tm3[3], h->tm3[4], h->tm3[5], p));                              \
   } while (0)
@@ -684,10 +697,19 @@ extern "C" int mvb_s1_begin(mvb_s1* h, int32_t utt, int32_t first_token, int32_t
   if (!h || !p) return fail(MVB_ERR_ARG, "null argument");
   if (utt < 0 || utt >= h->cfg.max_utts) return fail(MVB_ERR_ARG, "utterance slot %d out of range", utt);
   if (pos < 0 || pos >= h->cfg.block_size) return fail(MVB_ERR_ARG, "position %d outside the context", pos);
-  k_begin<<<1, 32, 0, (cudaStream_t)stream>>>(h->st, utt, first_token, pos, to_dev(p), d_noise, d_forced, first_token >= 0);
+  k_begin<<<1, 32, 0, (cudaStream_t)stream>>>(h->st, utt, first_token, pos, to_dev(p), d_noise, d_forced, first_token >= 0,
+                                              h->cfg.max_new);
   h->launches++;
   CK(cudaGetLastError());
   return MVB_OK;
+}
+
+// per-utterance token budget (generate(): utils:196-204) and the step that row 0 of the staged noise belongs to
+__global__ void k_set_budget(S1State st, int utt, int budget) {
+  if (threadIdx.x == 0) st.budget[utt] = budget;
+}
+__global__ void k_set_noise_base(S1State st, int n_utts, int base) {
+  if ((int)threadIdx.x < n_utts) st.noise_base[threadIdx.x] = base;
 }
 
 static int sample_step(mvb_s1* h, cudaStream_t s, int n_utts) {
@@ -709,6 +731,11 @@ extern "C" int mvb_s1_decode(mvb_s1* h, int32_t n_utts, int32_t n_steps, void* s
   h->launches++;
   CK(cudaGetLastError());
   const bool use_c = h->path_c && h->pc_ok && 2 * n_utts <= PC_RPAD;
+  if (use_c) {
+    // The persistent kernel ACCUMULATES split-K partial logits (red.add); a prefill (mvb_s1_forward) leaves the last
+    // position's logits in the same rows, so they must be zero before the first fused step.
+    CK(cudaMemsetAsync(h->wsp<float>(h->L.logits), 0, sizeof(float) * 2 * (size_t)n_utts * h->cfg.vocab, s));
+  }
   for (int i = 0; i < n_steps; ++i) {
     if (use_c) {
       if (int e = launch_persistent(h, s, n_utts)) return e;
@@ -782,8 +809,8 @@ extern "C" int mvb_s1_fetch_sampled(mvb_s1* h, int32_t utt, int32_t* out_tokens,
 
 extern "C" int mvb_s1_generate(mvb_s1* h, int32_t n_utts, const int32_t* prompts, const int32_t* prompt_lens,
                                const float* spk_embs, const mvb_sampling* params, int32_t max_new_tokens,
-                               const float* noise, const int32_t* forced, int32_t* out_tokens, int32_t* out_lens,
-                               void* stream) {
+                               const float* noise, int32_t noise_on_device, const int32_t* forced, int32_t* out_tokens,
+                               int32_t* out_lens, void* stream) {
   if (!h || !prompts || !prompt_lens || !spk_embs || !params || !out_tokens || !out_lens)
     return fail(MVB_ERR_ARG, "null argument");
   const mvb_s1_config& c = h->cfg;
@@ -800,11 +827,19 @@ extern "C" int mvb_s1_generate(mvb_s1* h, int32_t n_utts, const int32_t* prompts
     budget[i] = room;
   }
   const int V = c.vocab;
-  float* d_noise = nullptr;
-  if (noise) {
-    CK(cudaMalloc(&d_noise, sizeof(float) * (size_t)n_utts * max_new_tokens * V));
-    CK(cudaMemcpyAsync(d_noise, noise, sizeof(float) * (size_t)n_utts * max_new_tokens * V, cudaMemcpyHostToDevice, s));
-  }
+  // Exp(1) draws: a device buffer is used in place; a host buffer is staged one burst of decode steps at a time
+  // into the workspace (no allocation inside the call).
+  const bool stage_noise = noise != nullptr && !noise_on_device;
+  float* d_stage = h->wsp<float>(h->L.stage_noise);
+  auto stage_rows = [&](int step0, int rows) -> int {
+    for (int i = 0; i < n_utts; ++i)
+      CK(cudaMemcpyAsync(d_stage + (size_t)i * GEN_BURST * V, noise + ((size_t)i * max_new_tokens + step0) * V,
+                         sizeof(float) * (size_t)rows * V, cudaMemcpyHostToDevice, s));
+    k_set_noise_base<<<1, 64, 0, s>>>(h->st, n_utts, step0);
+    h->launches++;
+    CK(cudaGetLastError());
+    return MVB_OK;
+  };
   int* d_forced = h->wsp<int>(h->L.stage_forced);
   if (forced) CK(cudaMemcpyAsync(d_forced, forced, sizeof(int) * (size_t)n_utts * max_new_tokens, cudaMemcpyHostToDevice, s));
   int* d_idx = h->wsp<int>(h->L.stage_idx);
@@ -822,8 +857,18 @@ extern "C" int mvb_s1_generate(mvb_s1* h, int32_t n_utts, const int32_t* prompts
     poff += T;
     if ((rc = mvb_s1_set_speaker(h, i, d_spk + (size_t)i * c.spk_dim, s))) break;
     mvb_sampling sp = params[i];
-    if ((rc = mvb_s1_begin(h, i, -1, 0, &sp, d_noise ? d_noise + (size_t)i * max_new_tokens * V : nullptr,
-                           forced ? d_forced + (size_t)i * max_new_tokens : nullptr, s))) break;
+    const float* dn = nullptr;
+    if (stage_noise) dn = d_stage + (size_t)i * GEN_BURST * V;
+    else if (noise) dn = noise + (size_t)i * max_new_tokens * V;
+    if ((rc = mvb_s1_begin(h, i, -1, 0, &sp, dn, forced ? d_forced + (size_t)i * max_new_tokens : nullptr, s))) break;
+    k_set_budget<<<1, 32, 0, s>>>(h->st, i, budget[i]);
+    h->launches++;
+    if (budget[i] > max_budget) max_budget = budget[i];
+  }
+  if (rc == MVB_OK && stage_noise) rc = stage_rows(0, 1);      // row 0 feeds the post-prefill samples below
+  for (int i = 0; i < n_utts && rc == MVB_OK; ++i) {
+    const int T = prompt_lens[i];
+    int* di = d_idx + (size_t)i * 2 * c.block_size;
     if ((rc = mvb_s1_forward(h, i, di, T, 0, nullptr, 0, s))) break;  // prefill (utils:123-132)
     // first token sampled from the last prefill position (utils:211-212)
     SampleP spp{};
@@ -833,16 +878,17 @@ extern "C" int mvb_s1_generate(mvb_s1* h, int32_t n_utts, const int32_t* prompts
     k_sample<<<1, SAMP_THREADS, 0, s>>>(spp, h->st);  // slot_map[0] == i after the prefill
     h->launches++;
     if (cudaGetLastError() != cudaSuccess) { rc = fail(MVB_ERR_CUDA, "sampler launch failed"); break; }
-    if (budget[i] > max_budget) max_budget = budget[i];
   }
-  // decode_n_tokens: at most budget-1 further steps, all utterances advance together with their own
-  // positions; per-utterance budgets are enforced by the done latch (n_gen >= budget -> host stops reading).
+  // decode_n_tokens: at most budget-1 further steps, all utterances advance together with their own positions;
+  // per-utterance budgets and the end of the context are latched on the device (done flag).
   if (rc == MVB_OK) {
-    int remaining = max_budget - 1;
+    int remaining = max_budget - 1, step0 = 1;
     while (remaining > 0 && rc == MVB_OK) {
-      const int burst = remaining < 32 ? remaining : 32;
+      const int burst = remaining < GEN_BURST ? remaining : GEN_BURST;
+      if (stage_noise && (rc = stage_rows(step0, burst))) break;
       rc = mvb_s1_decode(h, n_utts, burst, s);
       remaining -= burst;
+      step0 += burst;
       if (rc) break;
       CK(cudaMemcpyAsync(h->h_flags, h->st.done, sizeof(int) * n_utts, cudaMemcpyDeviceToHost, s));
       CK(cudaStreamSynchronize(s));
@@ -863,6 +909,5 @@ extern "C" int mvb_s1_generate(mvb_s1* h, int32_t n_utts, const int32_t* prompts
     }
     CK(cudaStreamSynchronize(s));
   }
-  if (d_noise) cudaFree(d_noise);
   return rc;
 }

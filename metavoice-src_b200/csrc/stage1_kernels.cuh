@@ -30,6 +30,8 @@ struct S1State {
   const float** noise;  // [max_utts] optional Exp(1) draws [max_new, vocab]
   const int** forced;   // [max_utts] optional teacher-forced tokens [max_new]
   unsigned* attn_ticket;  // [2*max_utts*n_head] split-KV arrival counters
+  int* budget;          // [max_utts] tokens this utterance may produce (generate(): min(T + max_new, block) - T, utils:196-204)
+  int* noise_base;      // [max_utts] generation step that row 0 of noise[u] belongs to (host-staged noise arrives in chunks)
   int max_new, block_size;
 };
 
@@ -57,14 +59,16 @@ __global__ void k_set_input(S1State st, int utt, const int* __restrict__ idx, in
 }
 
 __global__ void k_begin(S1State st, int utt, int first_token, int pos, SamplingDev sp, const float* noise,
-                        const int* forced, int has_first) {
+                        const int* forced, int has_first, int budget) {
   if (threadIdx.x == 0) {
     st.samp[utt] = sp;
     st.noise[utt] = noise;
+    st.noise_base[utt] = 0;
     st.forced[utt] = forced;
     st.done[utt] = 0;
     st.n_gen[utt] = 0;
     st.pos[utt] = pos;
+    st.budget[utt] = budget;
     if (has_first) {
       st.row_tok[2 * utt] = first_token;
       st.row_tok[2 * utt + 1] = first_token;
@@ -512,11 +516,17 @@ __global__ void __launch_bounds__(SAMP_THREADS) k_sample(SampleP p, S1State st) 
   const float* lc = p.logits;
   if (p.decode_mode) {
     u = st.slot_map[blockIdx.x];
-    if (st.done[u]) return;
+    lc = p.logits + (size_t)(2 * u) * V;
+    if (st.done[u]) {
+      // a finished utterance still rides along in the batch (its rows are recomputed at a frozen position): hand its
+      // logits rows back zeroed so the persistent kernel's red.add accumulation starts from zero every step
+      float* z = const_cast<float*>(lc);
+      for (int v = tid; v < 2 * V; v += SAMP_THREADS) z[v] = 0.f;
+      return;
+    }
     sp = st.samp[u];
     step = (unsigned long long)st.n_gen[u];
-    noise = st.noise[u] ? st.noise[u] + (size_t)step * V : nullptr;
-    lc = p.logits + (size_t)(2 * u) * V;
+    noise = st.noise[u] ? st.noise[u] + (size_t)(st.n_gen[u] - st.noise_base[u]) * V : nullptr;
   }
   const float* lu = lc + V;
 
@@ -685,10 +695,14 @@ __global__ void __launch_bounds__(SAMP_THREADS) k_sample(SampleP p, S1State st) 
         st.gen_tokens[(size_t)u * st.max_new + n] = fed;
         st.row_tok[2 * u] = fed;
         st.row_tok[2 * u + 1] = fed;
+        // Latch termination (utils:161 EOA; utils:196-204 token budget; context end) and keep the position inside the
+        // cache: a finished utterance is re-run at its last valid slot while the rest of the batch continues, so no
+        // body ever reads pos_emb[block_size] or appends K/V past slot block_size - 1.
         const int np = st.pos[u] + 1;
-        st.pos[u] = np;
+        const bool stop = fed == sp.end_of_audio || np >= st.block_size || n + 1 >= st.max_new || n + 1 >= st.budget[u];
+        if (!stop) st.pos[u] = np;
         st.n_gen[u] = n + 1;
-        if (fed == sp.end_of_audio || np >= st.block_size || n + 1 >= st.max_new) st.done[u] = 1;
+        if (stop) st.done[u] = 1;
       }
     }
   }

@@ -52,7 +52,7 @@ SIGNATURES = {
     "mvb_s1_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(Sampling), C.c_void_p, C.c_uint64, C.c_void_p,
                                 C.c_void_p, C.c_void_p]),
     "mvb_s1_generate": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Sampling),
-                                  C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                  C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mvb_s1_decode": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "mvb_s1_begin": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(Sampling), C.c_void_p,
                                C.c_void_p, C.c_void_p]),
@@ -74,12 +74,11 @@ SIGNATURES = {
     "mvb_voc_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "mvb_linear": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_float,
                              C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
-}
-# helper exported for the parity tests only (not part of the drop-in surface)
-TEST_SIGNATURES = {
+    # test / debug hooks (declared in the header as such)
     "mvb_s1_fetch_sampled": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "mvb_s1_trace_fetch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
 }
+ABI_VERSION = 2
 
 _lib = None
 
@@ -97,12 +96,11 @@ def load() -> C.CDLL:
         raise MvbError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                        "(libmvb200 has no CPU or PyTorch fallback)")
     lib = C.CDLL(LIB_PATH)
-    for table in (SIGNATURES, TEST_SIGNATURES):
-        for name, (res, args) in table.items():
-            fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
-            fn.restype = res
-            fn.argtypes = args
-    if lib.mvb_abi_version() != 1:
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mvb_abi_version() != ABI_VERSION:
         raise MvbError("libmvb200 ABI version mismatch")
     _lib = lib
     return lib

@@ -96,22 +96,50 @@ def generate(model: Transformer, prompt: torch.Tensor, spk_emb: torch.Tensor, *,
              forced: Optional[torch.Tensor] = None, **sampling_kwargs) -> torch.Tensor:
     """Same contract as the reference: returns prompt ++ generated tokens (EOA included if emitted).
     The whole decode loop (sampler, EOA latch, position bump) runs on the device; ``noise`` / ``forced``
-    are parity-test hooks (Exp(1) draws in the reference's call order / teacher-forced feedback)."""
+    are parity-test hooks (Exp(1) draws in the reference's call order / teacher-forced feedback).
+    ``callback`` is invoked once per generated token, in order, like the reference's (utils:168) -- after the device
+    loop has finished, since there is no per-token host round trip to hook into."""
     out = generate_batch(model, [prompt], spk_emb.reshape(1, -1), max_new_tokens=max_new_tokens,
                          end_of_audio_token=end_of_audio_token, noise=None if noise is None else noise[None],
                          forced=None if forced is None else forced[None], **sampling_kwargs)[0]
+    for t in out[1:]:          # decode_n_tokens calls back for every token after the prefill sample (utils:166-168)
+        callback(t.view(1))
     seq = torch.cat([prompt.to(torch.int32).cpu(), out]).to(prompt.device)
     return seq
+
+
+def draw_reference_noise(n_utts: int, n_steps: int, vocab: int, device, rng: str) -> torch.Tensor:
+    """The Exp(1) draws ``multinomial_sample_one_no_sync`` makes (utils:61-65: ``torch.empty_like(probs).exponential_(1)``,
+    ONE [vocab]-sized draw per generated token) taken from torch's global generator in the reference's call order, so
+    that ``torch.manual_seed(s); generate(...)`` yields the reference's token ids.
+      rng="torch"     : the generator of the device the model lives on -- what the reference consumes when it runs on
+                        a GPU (one exponential_ call per token: CUDA Philox offsets advance per call);
+      rng="torch-cpu" : the CPU generator -- what the reference consumes when it runs on CPU (the golden vectors under
+                        tests/golden were produced that way).  Returns a DEVICE tensor [n_utts, n_steps, vocab]."""
+    if rng == "torch-cpu":
+        q = torch.stack([torch.stack([torch.empty(vocab).exponential_(1) for _ in range(n_steps)]) for _ in range(n_utts)])
+        return q.to(device)
+    q = torch.empty((n_utts, n_steps, vocab), dtype=torch.float32, device=device)
+    for u in range(n_utts):
+        for s in range(n_steps):
+            q[u, s].exponential_(1)
+    return q
 
 
 @torch.no_grad()
 def generate_batch(model: Transformer, prompts, spk_embs: torch.Tensor, *, max_new_tokens: Optional[int] = None,
                    end_of_audio_token: int = 2048, noise=None, forced=None, seed: Optional[int] = None,
-                   guidance_scale=3.0, temperature=1.0, top_p=None, top_k=None, return_sampled: bool = False):
+                   guidance_scale=3.0, temperature=1.0, top_p=None, top_k=None, return_sampled: bool = False,
+                   rng: Optional[str] = None):
     """N independent utterances decoded together with per-utterance positions (the batching semantics of
     fam/llm/mixins/causal.py:179-287, numerically equal to running each utterance alone).  Goes through the
     HOST-buffer plugin call ``mvb_s1_generate``: prompts/speakers are copied host->device and the tokens
-    device->host inside the call."""
+    device->host inside the call.
+
+    Randomness: ``noise`` (explicit Exp(1) draws) > ``seed`` (on-device Philox stream keyed by it) > ``rng``.
+    With neither ``noise`` nor ``seed`` the draws come from torch's global generator exactly where the reference
+    takes them (``rng="torch"``, see ``draw_reference_noise``); ``rng="philox"`` selects the on-device stream keyed
+    from torch's generator instead (no noise buffer, used by the throughput benchmark)."""
     n = len(prompts)
     if n > model.max_utts:
         raise ValueError(f"{n} utterances exceed the {model.max_utts} slots set up by setup_caches")
@@ -127,8 +155,13 @@ def generate_batch(model: Transformer, prompts, spk_embs: torch.Tensor, *, max_n
     max_new = min(max_new, model._cfg.max_new)
     flat = np.concatenate([p.detach().cpu().numpy().astype(np.int32).reshape(-1) for p in prompts])
     spk = np.ascontiguousarray(spk_embs.detach().to("cpu", torch.float32).numpy().reshape(n, -1))
+    if rng is None:
+        rng = "philox" if seed is not None else "torch"
+    d_noise = None
+    if noise is None and seed is None and rng in ("torch", "torch-cpu"):
+        d_noise = draw_reference_noise(n, max_new, model.config.vocab_size, model.device, rng)
     if seed is None:  # tie the on-device Philox stream to torch's global generator (torch.manual_seed reproducible)
-        seed = int(torch.randint(0, 2**62, (1,)).item())
+        seed = int(torch.randint(0, 2**62, (1,)).item()) if d_noise is None else 0
     params = (_lib.Sampling * n)(*[_sampling_struct(guidance_scale, temperature, top_p, top_k, end_of_audio_token,
                                                     seed + 7919 * i) for i in range(n)])
     out = np.zeros((n, max_new), dtype=np.int32)
@@ -140,8 +173,9 @@ def generate_batch(model: Transformer, prompts, spk_embs: torch.Tensor, *, max_n
     if fc is not None:
         assert fc.shape == (n, max_new), fc.shape
     vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
-    _lib.check(model._lib.mvb_s1_generate(model.handle, n, vp(flat), vp(lens), vp(spk), params, max_new, vp(nz), vp(fc),
-                                          vp(out), vp(out_lens), model._stream()))
+    noise_arg, on_dev = (C.c_void_p(d_noise.data_ptr()), 1) if d_noise is not None else (vp(nz), 0)
+    _lib.check(model._lib.mvb_s1_generate(model.handle, n, vp(flat), vp(lens), vp(spk), params, max_new, noise_arg, on_dev,
+                                          vp(fc), vp(out), vp(out_lens), model._stream()))
     fed = [torch.from_numpy(out[i, :out_lens[i]].copy()) for i in range(n)]
     if not return_sampled:
         return fed

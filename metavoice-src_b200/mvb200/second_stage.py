@@ -45,6 +45,18 @@ def tilted_decode(hier: Sequence[Sequence[int]], end_of_audio_token: int = PAD):
     return text[:-1], out
 
 
+def build_stage2_input(text_ids: Sequence[int], codes: Sequence[Sequence[int]], block_size: int, pad: int = PAD) -> torch.Tensor:
+    """The two input hierarchies of ``Model.non_causal_sample`` (inference.py:283-306): hierarchy 0 = text ++ codebook 0
+    ++ pad, hierarchy 1 = pad x len(text) ++ codebook 1 ++ pad, each padded with ``pad`` / cut to ``block_size``."""
+    h0 = list(text_ids) + list(codes[0]) + [pad]
+    h1 = [pad] * len(text_ids) + list(codes[1]) + [pad]
+    rows = []
+    for h in (h0, h1):
+        assert len(h) == len(h0)
+        rows.append(h + [pad] * (block_size - len(h)) if len(h) < block_size else h[:block_size])
+    return torch.tensor(rows, dtype=torch.int32)
+
+
 _GLOBAL = lambda n_in, n_out: ([f"transformer.wtes.{i}.weight" for i in range(n_in)] +
                                ["transformer.wpe.weight", "speaker_cond_pos.weight", "transformer.ln_f.weight"] +
                                [f"lm_heads.{i}.weight" for i in range(n_out)])
@@ -60,6 +72,9 @@ class SecondStage:
             raise ValueError("second-stage checkpoint must be non-causal")
         if a.get("norm_type") != "rmsnorm" or a.get("nonlinearity_type") != "swiglu" or a.get("bias", False):
             raise NotImplementedError("libmvb200 stage 2 supports rmsnorm + swiglu + bias=False checkpoints")
+        if not a.get("spk_emb_on_text", True):
+            # model.py:104-107: the reference itself refuses a non-causal model with spk_emb_on_text=False
+            raise NotImplementedError("spk_emb_on_text=False is not supported for the non-causal second stage (model.py:104-107)")
         sd = {(k[len("_orig_mod."):] if k.startswith("_orig_mod.") else k): v for k, v in checkpoint["model"].items()}
         self.args, self.device = a, torch.device(device)
         self.n_in, self.n_out = len(a["vocab_sizes"]), len(a["target_vocab_sizes"])
@@ -106,13 +121,7 @@ class SecondStage:
 
     # inference.py:283-301
     def build_input(self, text_ids: Sequence[int], codes: Sequence[Sequence[int]]) -> torch.Tensor:
-        h0 = list(text_ids) + list(codes[0]) + [PAD]
-        h1 = [PAD] * len(text_ids) + list(codes[1]) + [PAD]
-        rows = []
-        for h in (h0, h1):
-            assert len(h) == len(h0)
-            rows.append(h + [PAD] * (self.block_size - len(h)) if len(h) < self.block_size else h[:self.block_size])
-        return torch.tensor(rows, dtype=torch.int32)
+        return build_stage2_input(text_ids, codes, self.block_size)
 
     @torch.no_grad()
     def forward_tokens(self, idx: torch.Tensor, speaker_embs: Optional[torch.Tensor], temperature: float = 1.0,

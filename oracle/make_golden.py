@@ -148,4 +148,4 @@ if __name__ == "__main__":
     golden_sampler()
     golden_stage1(synth.TINY, "tiny", T=12, n_new=24, keep_steps=[0, 1, 2, 3, 8, 23])
     if not a.skip_full:
-        golden_stage1(synth.FULL, "full", T=32, n_new=65, keep_steps=[0, 1, 8, 64])
+        golden_stage1(synth.FULL, "full", T=48, n_new=256, keep_steps=[0, 1, 8, 64, 255])

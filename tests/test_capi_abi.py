@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for name in _declared():
         assert hasattr(lib, name), f"{name} declared in include/mvb200.h but not exported"
     assert set(_declared()) == set(_lib.SIGNATURES), "python binding table out of sync with the header"
-    assert lib.mvb_abi_version() == 1
+    assert lib.mvb_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_config_validation_without_gpu():

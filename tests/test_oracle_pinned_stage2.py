@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from mvb200 import synth
-from mvb200.second_stage import flattened_interleaved_decode, tilted_decode
+from mvb200.second_stage import build_stage2_input, flattened_interleaved_decode, tilted_decode
 from oracle import ref_harness, stage2_port as P
 
 
@@ -56,3 +56,36 @@ def test_input_builder_layout():
     assert idx.tolist() == [[1100, 1537, 1, 2, 3, 1024, 1024, 1024], [1024, 1024, 4, 5, 6, 1024, 1024, 1024]]
     idx = P.build_input([1100, 1537], list(range(10)), list(range(10)), 8)      # truncation to block_size
     assert idx.shape == (2, 8) and idx[0, -1] == 5
+
+
+@pytest.mark.parametrize("tag", ["tiny", "full"])
+def test_product_input_builder_matches_reference_golden(golden_dir, tag):
+    """a13: the PRODUCT builder (mvb200.second_stage.build_stage2_input, what SecondStage.build_input calls) against
+    the tensor the reference's own Model.non_causal_sample built (oracle/make_golden_stage2_input.py executes
+    fam/llm/inference.py:264-306): padded, cut-by-one, truncated and exact-fit cases."""
+    g = np.load(f"{golden_dir}/stage2_input.npz")
+    bs = int(g[f"{tag}_block"])
+    ref = g[f"{tag}_in_x"]
+    for i in range(ref.shape[0]):
+        got = build_stage2_input(g[f"{tag}_text_{i}"].tolist(), g[f"{tag}_codes_{i}"].tolist(), bs)
+        assert got.shape == (2, bs) and got.dtype == torch.int32
+        assert np.array_equal(got.numpy(), ref[i]), f"case {i}"
+        assert np.array_equal(P.build_input(g[f"{tag}_text_{i}"].tolist(), *g[f"{tag}_codes_{i}"].tolist(), bs).numpy(), ref[i])
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not mounted (GPU box)")
+def test_product_input_builder_matches_live_reference():
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("mk_s2in", os.path.join(os.path.dirname(P.__file__), "make_golden_stage2_input.py"))
+    mk = importlib.util.module_from_spec(spec); spec.loader.exec_module(mk)
+    from mvb200.tokenise import TrainedBPETokeniser
+    tok = TrainedBPETokeniser(**synth.synthetic_tokenizer_meta(n_text_tokens=512, offset=1025))
+    Model = mk.reference_model_class()
+    g = torch.Generator().manual_seed(77)
+    texts = ["a b c", "the quick brown fox", "x"]
+    codes = [torch.randint(0, 1024, (1, 2, n), generator=g) for n in (10, 300, 255)]
+    in_x = mk.reference_in_x(Model, tok, texts, codes, 256)
+    for i in range(3):
+        got = build_stage2_input(tok.encode(texts[i]), codes[i][0].tolist(), 256)
+        assert torch.equal(got.long(), in_x[i])

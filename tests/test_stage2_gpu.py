@@ -28,9 +28,24 @@ def test_stage2_logits_and_tokens_vs_reference_golden(golden_dir, tag, dims):
     print(f"stage-2 {tag}: logits rel err {err:.2e}")
     assert err < 1e-3
     ref_t = torch.from_numpy(g[f"{tag}_tokens"])
-    agree = float((toks[0].cpu() == ref_t).float().mean())
-    print(f"stage-2 {tag}: {agree * 100:.2f}% of {ref_t.numel()} sampled ids identical to the reference")
-    assert agree > 0.995    # near-ties at the top-k boundary / exp-race may flip a handful of 6144 draws
+    ours = toks[0].cpu()
+    diff = (ours != ref_t).nonzero().tolist()
+    print(f"stage-2 {tag}: {ref_t.numel() - len(diff)}/{ref_t.numel()} sampled ids identical to the reference")
+    # a15 gate: identical ids, or -- for every differing draw -- an explicit audit that it is a tie the two
+    # implementations may legitimately break differently given logits that agree to ~3e-6: either the exp-race scores
+    # p/q of the two candidates are within 1e-3 of each other, or one candidate sits on the top-k(200) boundary
+    # (its logit within 1e-4 * max|logit| of the 200th largest).
+    lgc = lg.cpu()
+    for h, pos in diff:
+        row = lgc[h, pos].double()
+        a, b = int(ours[h, pos]), int(ref_t[h, pos])
+        kth = torch.topk(row, 200).values[-1]
+        on_boundary = min(abs(float(row[a] - kth)), abs(float(row[b] - kth))) < 1e-4 * float(row.abs().max())
+        masked = torch.where(row < kth, torch.full_like(row, -float("inf")), row)
+        sc = torch.softmax(masked, -1) / noise[h, pos].double()
+        near_tie = float(min(sc[a], sc[b]) / max(sc[a], sc[b])) > 1 - 1e-3
+        assert on_boundary or near_tie, f"draw ({h},{pos}): ours {a} vs reference {b} is not a tie"
+    assert len(diff) <= max(1, ref_t.numel() // 1000)
 
 
 def test_stage2_batch_and_pipeline_shapes():
