@@ -8,11 +8,13 @@ top_p 0.95, guidance 3.0, temperature 1.0, bf16 weights + bf16 KV cache) on ever
   value  : whole-job stage-1 tokens/s with inputs already resident in HBM (prefill + decode on device)
   e2e    : same metric through the reference-facing plugin call mvb_s1_generate with HOST buffers
            (prompt/speaker host->device, tokens device->host inside the timed region)
-  roofline: the decode step (persistent fused kernel + sampler), algorithmic bytes / CUDA-event time vs measured HBM peak
-  cpu_baseline: the oracle port of the reference's CPU path, timed on this box's host cores (bounded sample)
+  roofline: the persistent fused decode kernel (one launch = a burst of decode positions incl. the on-device sampler),
+            algorithmic bytes / CUDA-event time vs measured HBM peak
+  cpu_baseline: the reference's own CPU code (oracle/_ref, vendored by oracle/build_ref.py) timed on this box's host
+            cores on a bounded sample; falls back to the oracle port only when oracle/_ref is absent
+  configs : the other BASELINE configurations on the same engine (batch 8 mixed-length, 6 x 10 s long-form batch)
 
-`--impl reference` times the reference's CPU implementation (oracle port; the Python reference cannot travel
-to the GPU box) on the same metric; under torchrun only rank 0 runs it.
+`--impl reference` times the reference's CPU implementation on the same metric; under torchrun only rank 0 runs it.
 """
 from __future__ import annotations
 
@@ -32,6 +34,8 @@ for p in (ROOT, os.path.join(ROOT, "metavoice-src_b200")):
 import torch  # noqa: E402
 
 T_PROMPT, N_NEW = 48, 750
+MIX_LENS = [24, 32, 48, 64, 80, 96, 112, 120]      # BASELINE configs[2]: batch 8, mixed-length prompts
+LONG_UTTS, LONG_T, LONG_NEW = 6, 64, 1500          # BASELINE configs[3]: 60 s = 6 chunks x 10 s submitted as one batch
 SAMPLING = dict(guidance_scale=3.0, temperature=1.0, top_p=0.95)
 W_BYTES = 2_476_953_600            # stage-1 weight bytes streamed per decode step
 KV_BYTES_PER_POS = 393_216         # K+V bytes per cached position per utterance (2 CFG rows, 24 layers, bf16)
@@ -115,20 +119,71 @@ def build_engine(device, utts, rank, world):
     return model, time.time() - t0, bcast_ms
 
 
-def resident_pass(model, d_idx, d_spk, utts, seed):
+def resident_pass(model, d_idx, d_spk, lens, n_new, seed):
     """Prefill + decode with inputs already in HBM; returns tokens generated (device time is measured by the caller)."""
     import ctypes as C
     from mvb200 import _lib
     lib, h, st = model._lib, model.handle, model._stream()
+    utts = len(lens)
     for u in range(utts):
         sp = _lib.Sampling(SAMPLING["guidance_scale"], SAMPLING["temperature"], SAMPLING["top_p"], 0, 9999, seed + u)
         _lib.check(lib.mvb_s1_set_speaker(h, u, d_spk[u].data_ptr(), st))
         _lib.check(lib.mvb_s1_begin(h, u, -1, 0, C.byref(sp), None, None, st))
-        _lib.check(lib.mvb_s1_forward(h, u, d_idx[u].data_ptr(), T_PROMPT, 0, None, 0, st))
-    # decode() = N_NEW x (body, sampler).  Its first body replays the last prefill position (idempotent cache
-    # write) so that the first token is sampled from the prefill logits exactly as generate() does (utils:211).
-    _lib.check(lib.mvb_s1_decode(h, utts, N_NEW, st))
-    return utts * N_NEW
+        _lib.check(lib.mvb_s1_forward(h, u, d_idx[u].data_ptr(), lens[u], 0, None, 0, st))
+    # decode() = n_new x (body, sampler) in ONE persistent launch.  Its first body replays the last prefill position
+    # (idempotent cache write) so that the first token is sampled from the prefill logits exactly as generate() does (utils:211).
+    _lib.check(lib.mvb_s1_decode(h, utts, n_new, st))
+    return utts * n_new
+
+
+def tokens_generated(model, utts):
+    """n_gen of every utterance as the device recorded it (checked once per leg, outside the timed region)."""
+    import ctypes as C
+    from mvb200 import _lib
+    out = []
+    for u in range(utts):
+        n, d = C.c_int32(0), C.c_int32(0)
+        _lib.check(model._lib.mvb_s1_fetch(model.handle, u, None, 0, C.byref(n), C.byref(d), model._stream()))
+        out.append(int(n.value))
+    return out
+
+
+def step_roofline(model, lens, n_new, reps, device):
+    """One persistent launch of `reps` decode positions around the middle of the utterance (CUDA events on the launching
+    stream): algorithmic bytes = reps x weights + K/V of every cached position read + the appended position written."""
+    import ctypes as C
+    from mvb200 import _lib
+    utts = len(lens)
+    lib, h, st = model._lib, model.handle, model._stream()
+    starts = [T + n_new // 2 - reps // 2 for T in lens]
+    for u in range(utts):
+        sp = _lib.Sampling(3.0, 1.0, 0.95, 0, 9999, 5 + u)
+        _lib.check(lib.mvb_s1_begin(h, u, 100 + u, starts[u], C.byref(sp), None, None, st))
+    _lib.check(lib.mvb_s1_decode(h, utts, 8, st))                      # warm
+    for u in range(utts):
+        sp = _lib.Sampling(3.0, 1.0, 0.95, 0, 9999, 5 + u)
+        _lib.check(lib.mvb_s1_begin(h, u, 100 + u, starts[u], C.byref(sp), None, None, st))
+    torch.cuda.synchronize(device)
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    _lib.check(lib.mvb_s1_decode(h, utts, reps, st))
+    r1.record()
+    torch.cuda.synchronize(device)
+    ms = r0.elapsed_time(r1)
+    nbytes = 0
+    for i in range(reps):
+        nbytes += W_BYTES + sum(KV_BYTES_PER_POS * (s0 + i) + KV_BYTES_PER_POS for s0 in starts)
+    return ms, nbytes, [s0 + reps // 2 for s0 in starts]
+
+
+def ncu_traffic_per_position():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the persistent kernel per decode position, from the committed
+    `ncu --set full` capture of a short launch (profiles/r2_ncu_traffic.json written by tools/ncu_traffic.py)."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return None
 
 
 def main():
@@ -140,6 +195,7 @@ def main():
     ap.add_argument("--utts-per-gpu", type=int, default=1)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-pipeline", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true", help="skip the batch-8 / long-form legs (BASELINE configs[2], [3])")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -156,13 +212,17 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     utts = a.utts_per_gpu
-    model, build_s, bcast_ms = build_engine(device, utts, rank, world)
+    slots = utts if a.skip_configs else max(utts, len(MIX_LENS))
+    model, build_s, bcast_ms = build_engine(device, slots, rank, world)
     from mvb200 import synth, fast_inference_utils as U
 
-    prompts = [synth.synthetic_prompt(T_PROMPT, seed=7 + rank * 64 + u) for u in range(utts)]
-    spk = torch.cat([synth.synthetic_speaker(seed=11 + rank * 64 + u) for u in range(utts)])
-    d_idx = [p.view(1, -1).repeat(2, 1).to(device).contiguous() for p in prompts]
-    d_spk = [spk[u].to(device).contiguous() for u in range(utts)]
+    def inputs(lens, base):
+        pr = [synth.synthetic_prompt(T, seed=base + rank * 64 + u) for u, T in enumerate(lens)]
+        sp = torch.cat([synth.synthetic_speaker(seed=base + 4 + rank * 64 + u) for u in range(len(lens))])
+        return pr, sp, [q.view(1, -1).repeat(2, 1).to(device).contiguous() for q in pr], [sp[u].to(device).contiguous() for u in range(len(lens))]
+
+    lens = [T_PROMPT] * utts
+    prompts, spk, d_idx, d_spk = inputs(lens, 7)
     h_spk_pinned = spk.pin_memory()
 
     def barrier():
@@ -172,9 +232,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    def timed_resident(lens_, d_idx_, d_spk_, n_new, steps, warmup, seed0):
+        for w in range(warmup):
+            resident_pass(model, d_idx_, d_spk_, lens_, n_new, seed0 + w)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        toks = 0
+        for k in range(steps):
+            toks += resident_pass(model, d_idx_, d_spk_, lens_, n_new, seed0 + 100 + k)
+        e1.record()
+        barrier()
+        assert tokens_generated(model, len(lens_)) == [n_new] * len(lens_)
+        return toks, e0.elapsed_time(e1)
+
     # ---- HBM-resident value ------------------------------------------------------------------
     for w in range(a.warmup):
-        resident_pass(model, d_idx, d_spk, utts, 1000 + w)
+        resident_pass(model, d_idx, d_spk, lens, N_NEW, 1000 + w)
     barrier()
     lc0 = model._lib.mvb_s1_launch_count(model.handle)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -182,35 +256,19 @@ def main():
         e0.record()
         toks = 0
         for k in range(a.steps):
-            toks += resident_pass(model, d_idx, d_spk, utts, 2000 + k)
+            toks += resident_pass(model, d_idx, d_spk, lens, N_NEW, 2000 + k)
         e1.record()
         barrier()
     launches = model._lib.mvb_s1_launch_count(model.handle) - lc0
     ms = e0.elapsed_time(e1)
+    assert tokens_generated(model, utts) == [N_NEW] * utts
 
-    # ---- decode-step roofline: CUDA events around graph replays at a fixed context length -----
-    import ctypes as C
+    # ---- decode roofline: one persistent launch of `reps` positions at mid-utterance context ----
     reps = 200
-    model._lib.mvb_s1_decode(model.handle, utts, 8, model._stream())
-    torch.cuda.synchronize(device)
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # rewind to mid-utterance so the KV term is representative (L ~ T + N_NEW/2)
-    resident_pass(model, d_idx, d_spk, utts, 1)  # leaves pos = T+N_NEW
-    from mvb200 import _lib
-    for u in range(utts):
-        sp = _lib.Sampling(3.0, 1.0, 0.95, 0, 9999, 5)
-        _lib.check(model._lib.mvb_s1_begin(model.handle, u, 100, T_PROMPT + N_NEW // 2 - reps // 2, C.byref(sp), None, None,
-                                           model._stream()))
-    torch.cuda.synchronize(device)
-    r0.record()
-    _lib.check(model._lib.mvb_s1_decode(model.handle, utts, reps, model._stream()))
-    r1.record()
-    torch.cuda.synchronize(device)
-    step_ms = r0.elapsed_time(r1) / reps
-    L_mid = T_PROMPT + N_NEW // 2
-    step_bytes = W_BYTES + utts * (KV_BYTES_PER_POS * L_mid + KV_BYTES_PER_POS)
+    launch_ms, launch_bytes, mids = step_roofline(model, lens, N_NEW, reps, device)
     peak, peak_src = measured_peaks()
-    achieved = step_bytes / (step_ms * 1e-3) / 1e9
+    achieved = launch_bytes / (launch_ms * 1e-3) / 1e9
+    ncu = ncu_traffic_per_position()
 
     # ---- e2e through the host-buffer plugin call ---------------------------------------------
     for w in range(max(1, a.warmup // 2)):
@@ -225,58 +283,47 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
-    # ---- whole implemented pipeline (host text-side inputs -> wav on host): stage-1 -> adapters -> stage-2 -> EnCodec decoder
+    # ---- the other BASELINE configurations on the same engine (device-timed, max over ranks) -----
+    cfg_times, cfg_info = [], {}
+    if not a.skip_configs:
+        # configs[2] / configs[4]: 8 mixed-length prompts per GPU, 750 tokens each, top-p sampling
+        pr8, sp8, di8, ds8 = inputs(MIX_LENS, 31)
+        t8, ms8 = timed_resident(MIX_LENS, di8, ds8, N_NEW, 2, 1, 6000)
+        l8_ms, l8_bytes, l8_mid = step_roofline(model, MIX_LENS, N_NEW, 100, device)
+        cfg_times.append(ms8)
+        cfg_info["batch8_mixed"] = {"workload": f"BASELINE configs[2]/[4]: {len(MIX_LENS)} utterances per GPU, prompts {MIX_LENS}, {N_NEW} tokens each, top_p 0.95",
+                                    "tokens_per_rank": t8, "roofline_frac": round(l8_bytes / (l8_ms * 1e-3) / 1e9 / peak, 4),
+                                    "ms_per_position": round(l8_ms / 100, 4), "context_len_mid": l8_mid}
+        if world == 1:
+            # configs[3]: 60 s of speech = 6 chunks x 10 s (T=64, 1500 tokens each) submitted as one batch
+            ll = [LONG_T] * LONG_UTTS
+            prl, spl, dil, dsl = inputs(ll, 51)
+            tl, msl = timed_resident(ll, dil, dsl, LONG_NEW, 1, 1, 7000)
+            cfg_info["longform_60s"] = {"workload": f"BASELINE configs[3]: {LONG_UTTS} chunks x {LONG_NEW} tokens (10 s each), T={LONG_T}, one batch on 1 GPU",
+                                        "value": round(tl / (msl * 1e-3), 1), "unit": "tokens/s",
+                                        "audio_sec_per_s_stage1": round(tl / (msl * 1e-3) / 150.0, 2), "ms_total": round(msl, 1)}
+
+    # ---- whole implemented pipeline (host text-side inputs -> wav on host) ------------------------------------------
     pipe = None
     if not a.skip_pipeline:
-        from mvb200.second_stage import SecondStage, flattened_interleaved_decode
-        from mvb200.vocoder import EncodecDecodeEngine
-        s2 = SecondStage(synth.stage2_checkpoint(synth.S2_FULL, 1), device=device, max_batch=1)
-        codec = EncodecDecodeEngine(synth.encodec_model_and_state_dict(0)[1], device=device, max_frames=1024)
-        frames = N_NEW // 2
-        text_ids = torch.randint(1025, 1537, (11,), generator=torch.Generator().manual_seed(5)).tolist() + [1537]
+        pipe = pipeline_leg(model, prompts, spk, h_spk_pinned, utts, a.steps, device, world, barrier)
 
-        def pipeline_pass(seed):
-            toks = U.generate_batch(model, prompts, h_spk_pinned, max_new_tokens=N_NEW, end_of_audio_token=9999, seed=seed, **SAMPLING)
-            secs, t_s2, t_voc = 0.0, 0.0, 0.0
-            for u in range(utts):
-                _, cb = flattened_interleaved_decode(toks[u].tolist())
-                cb = [(c + [7] * frames)[:frames] for c in cb]   # random-init weights do not alternate codebooks: pad/cut to 375 frames
-                t0 = time.perf_counter()
-                idx = s2.build_input(text_ids, cb)[None]
-                codes8 = torch.cat([idx[0, :, len(text_ids):len(text_ids) + frames].to(device),
-                                    s2.forward_tokens(idx, spk[u:u + 1], 1.0, 200, seed=seed)[0, :, len(text_ids):len(text_ids) + frames]])
-                codes8 = codes8.clamp_(0, 1023)
-                torch.cuda.synchronize(device); t1 = time.perf_counter()
-                wav = codec.decode(codes8).cpu()
-                t2 = time.perf_counter()
-                secs += wav.numel() / 24000.0; t_s2 += t1 - t0; t_voc += t2 - t1
-            return secs, t_s2, t_voc
-
-        pipeline_pass(1)
-        barrier()
-        t0 = time.perf_counter()
-        audio_s = s2_s = voc_s = 0.0
-        for k in range(a.steps):
-            r = pipeline_pass(5000 + k)
-            audio_s += r[0]; s2_s += r[1]; voc_s += r[2]
-        barrier()
-        pipe_s = time.perf_counter() - t0
-        pipe = {"audio_sec_per_s": round(audio_s * world / pipe_s, 3), "audio_s_per_step": round(audio_s / a.steps, 3),
-                "ms_per_step": {"total": round(pipe_s / a.steps * 1e3, 2), "stage2": round(s2_s / a.steps * 1e3, 2),
-                                "encodec_decoder": round(voc_s / a.steps * 1e3, 2)},
-                "coverage": "stage-1 (750 tokens) + token adapters + stage-2 (6 codebooks) + EnCodec SEANet decoder, wav copied to host; "
-                            "the multi-band-diffusion refinement and DeepFilterNet of the reference are NOT implemented"}
-
-    times = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=device)
+    times = torch.tensor([ms, e2e_s * 1e3] + cfg_times, dtype=torch.float64, device=device)
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = [float(x) for x in times.cpu()]
+    tl_ = [float(x) for x in times.cpu()]
+    ms_max, e2e_ms_max = tl_[0], tl_[1]
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
+    if "batch8_mixed" in cfg_info:
+        c = cfg_info["batch8_mixed"]
+        c["value"] = round(c.pop("tokens_per_rank") * world / (tl_[2] * 1e-3), 1)
+        c["unit"] = "tokens/s"
+        c["audio_sec_per_s_stage1"] = round(c["value"] / 150.0, 2)
     total_toks = toks * world
     value = total_toks / (ms_max * 1e-3)
     line = {
@@ -292,20 +339,65 @@ def main():
         "e2e": {"value": round(e2e_toks * world / (e2e_ms_max * 1e-3), 2), "unit": "tokens/s",
                 "h2d_bytes_per_step": int(utts * (T_PROMPT * 4 * 2 + 256 * 4 + 32)), "d2h_bytes_per_step": int(utts * (N_NEW * 4 + 8))},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_decode_persistent (one persistent kernel per token: 24 x {qkv, attention, wo, w1|w3, w2} + head) + k_sample",
+        "roofline": {"bound": "hbm",
+                     "kernel": f"k_decode_persistent: ONE launch = {reps} decode positions (24 x {{qkv, attention, wo, w1|w3, w2}} + head + on-device sampler each)",
                      "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": round(achieved / peak, 4),
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed `ncu --set full` capture
-                     # (profiles/r1_ncu_persistent_final_summary.md, context length 58: algorithmic bytes there = 2.500e9)
-                     "traffic": 2627800000, "traffic_context_len": 58, "bytes_per_launch": int(step_bytes),
-                     "ms_per_launch": round(step_ms, 4), "context_len": L_mid},
+                     "traffic": (int(ncu["dram_bytes_per_position"] * reps) if ncu else None),
+                     "traffic_source": (ncu.get("source") if ncu else None),
+                     "bytes_per_launch": int(launch_bytes), "ms_per_launch": round(launch_ms, 3),
+                     "positions_per_launch": reps, "ms_per_position": round(launch_ms / reps, 4), "context_len_mid": mids[0]},
         "clocks": clk.summary(),
         "init": {"build_s": round(build_s, 2), "nccl_broadcast_ms": bcast_ms},
+        "configs": cfg_info or None,
         "pipeline": pipe,
     }
     if not a.skip_cpu_baseline and world == 1:   # reported at N=1 only (rank 0 would otherwise hold the other ranks' cores)
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line))
+
+
+def pipeline_leg(model, prompts, spk, h_spk_pinned, utts, steps, device, world, barrier):
+    """stage-1 -> adapters -> stage-2 -> vocoder -> wav on host, audio-seconds per second with per-stage milliseconds."""
+    from mvb200 import synth, fast_inference_utils as U
+    from mvb200.second_stage import SecondStage, flattened_interleaved_decode
+    from mvb200.vocoder import EncodecDecodeEngine
+    s2 = SecondStage(synth.stage2_checkpoint(synth.S2_FULL, 1), device=device, max_batch=1)
+    codec = EncodecDecodeEngine(synth.encodec_model_and_state_dict(0)[1], device=device, max_frames=1024)
+    frames = N_NEW // 2
+    text_ids = torch.randint(1025, 1537, (11,), generator=torch.Generator().manual_seed(5)).tolist() + [1537]
+
+    def pipeline_pass(seed):
+        toks = U.generate_batch(model, prompts, h_spk_pinned, max_new_tokens=N_NEW, end_of_audio_token=9999, seed=seed, **SAMPLING)
+        secs, t_s2, t_voc = 0.0, 0.0, 0.0
+        for u in range(utts):
+            _, cb = flattened_interleaved_decode(toks[u].tolist())
+            cb = [(c + [7] * frames)[:frames] for c in cb]   # random-init weights do not alternate codebooks: pad/cut to 375 frames
+            t0 = time.perf_counter()
+            idx = s2.build_input(text_ids, cb)[None]
+            codes8 = torch.cat([idx[0, :, len(text_ids):len(text_ids) + frames].to(device),
+                                s2.forward_tokens(idx, spk[u:u + 1], 1.0, 200, seed=seed)[0, :, len(text_ids):len(text_ids) + frames]])
+            codes8 = codes8.clamp_(0, 1023)
+            torch.cuda.synchronize(device); t1 = time.perf_counter()
+            wav = codec.decode(codes8).cpu()
+            t2 = time.perf_counter()
+            secs += wav.numel() / 24000.0; t_s2 += t1 - t0; t_voc += t2 - t1
+        return secs, t_s2, t_voc
+
+    pipeline_pass(1)
+    barrier()
+    t0 = time.perf_counter()
+    audio_s = s2_s = voc_s = 0.0
+    for k in range(steps):
+        r = pipeline_pass(5000 + k)
+        audio_s += r[0]; s2_s += r[1]; voc_s += r[2]
+    barrier()
+    pipe_s = time.perf_counter() - t0
+    return {"audio_sec_per_s": round(audio_s * world / pipe_s, 3), "audio_s_per_step": round(audio_s / steps, 3),
+            "ms_per_step": {"total": round(pipe_s / steps * 1e3, 2), "stage2": round(s2_s / steps * 1e3, 2),
+                            "encodec_decoder": round(voc_s / steps * 1e3, 2)},
+            "coverage": "stage-1 (750 tokens) + token adapters + stage-2 (6 codebooks) + EnCodec SEANet decoder, wav copied to host; "
+                        "the multi-band-diffusion refinement and DeepFilterNet of the reference are NOT implemented"}
 
 
 def _oracle_stage1(dtype):
@@ -330,16 +422,51 @@ def effective_cores() -> int:
     return max(1, n)
 
 
-def cpu_baseline(budget_s=20.0, model=None):
-    """Oracle port of the reference's CPU path (bf16, its production dtype) on all usable host threads; bounded
-    sample of the same workload: prefill of the T=48 prompt, then decode steps until `budget_s` elapses.  The
-    metric is the reference's own (utils:437-438): generated tokens / wall time including the prefill."""
+def _reference_stage1():
+    """The reference's OWN fast path (fam.llm.fast_model.Transformer + fam.llm.fast_inference_utils.generate, bf16 = its
+    production dtype) from oracle/_ref (or /root/reference), or None when neither is present."""
+    try:
+        from oracle import ref_harness as R
+        if not R.runnable():
+            return None
+        from mvb200 import synth
+        fiu = R.reference_functions()
+        model = R.build_reference_model(synth.stage1_state_dict(synth.FULL, 0), synth.FULL, torch.bfloat16)
+        return fiu, model
+    except Exception as e:   # noqa: BLE001
+        sys.stderr.write(f"reference stage-1 unavailable ({e}); using the oracle port\n")
+        return None
+
+
+def cpu_baseline(budget_s=20.0, model=None, ref=None):
+    """The reference's CPU path on all usable host threads, on a bounded sample of the same workload: its own
+    generate() (prefill of the T=48 prompt + k decode steps, k sized to the time budget from a short calibration call).
+    Metric = the reference's own (utils:437-438): generated tokens / wall time including the prefill."""
     from mvb200 import synth
-    from oracle import stage1_port as P
     cores = effective_cores()
     torch.set_num_threads(cores)
-    m = model or _oracle_stage1(torch.bfloat16)
     prompt, spk = synth.synthetic_prompt(T_PROMPT), synth.synthetic_speaker().to(torch.bfloat16)
+    if ref is None and model is None:
+        ref = _reference_stage1()
+    if ref is not None:
+        fiu, rmodel = ref
+        kw = dict(temperature=torch.tensor(1.0, dtype=torch.bfloat16), top_p=torch.tensor(0.95, dtype=torch.bfloat16),
+                  guidance_scale=torch.tensor(3.0, dtype=torch.bfloat16), top_k=None)
+        with torch.no_grad():
+            torch.manual_seed(1337)
+            t0 = time.perf_counter()
+            fiu.generate(rmodel, prompt, spk, max_new_tokens=6, end_of_audio_token=9999, **kw)     # calibration (untimed)
+            per_tok = (time.perf_counter() - t0) / 6
+            k = int(max(8, min(N_NEW, budget_s / max(per_tok, 1e-3))))
+            t0 = time.perf_counter()
+            y = fiu.generate(rmodel, prompt, spk, max_new_tokens=k, end_of_audio_token=9999, **kw)
+            dt = time.perf_counter() - t0
+        n = int(y.numel()) - T_PROMPT
+        return {"value": round(n / dt, 3), "unit": "tokens/s", "cores": cores, "kind": "reference",
+                "sample": f"the reference's own generate() (oracle/_ref, bf16, torch CPU eager): prefill T={T_PROMPT} + {n - 1} decode "
+                          f"steps of the 750-token workload in {dt:.1f} s on {cores} threads (cgroup quota; nproc={os.cpu_count()})"}
+    from oracle import stage1_port as P
+    m = model or _oracle_stage1(torch.bfloat16)
     kw = dict(guidance_scale=torch.tensor(3.0, dtype=torch.bfloat16), temperature=torch.tensor(1.0, dtype=torch.bfloat16),
               top_p=torch.tensor(0.95, dtype=torch.bfloat16))
     torch.manual_seed(1337)
@@ -354,23 +481,24 @@ def cpu_baseline(budget_s=20.0, model=None):
             n += 1; pos += 1
     dt = time.perf_counter() - t0
     return {"value": round(n / dt, 3), "unit": "tokens/s", "cores": cores, "kind": "port",
-            "sample": f"prefill T={T_PROMPT} + {n - 1} decode steps of the 750-token workload in {dt:.1f} s, bf16, torch CPU "
-                      f"({cores} threads = cgroup quota; nproc={os.cpu_count()})"}
+            "sample": f"oracle port (oracle/_ref absent): prefill T={T_PROMPT} + {n - 1} decode steps of the 750-token workload in {dt:.1f} s, "
+                      f"bf16, torch CPU ({cores} threads = cgroup quota; nproc={os.cpu_count()})"}
 
 
 def reference_arm(a):
-    m = _oracle_stage1(torch.bfloat16)
+    ref = _reference_stage1()
+    m = None if ref is not None else _oracle_stage1(torch.bfloat16)
     for _ in range(min(a.warmup, 1)):
-        cpu_baseline(3.0, m)
+        cpu_baseline(3.0, m, ref)
     t0 = time.perf_counter()
-    vals = [cpu_baseline(max(4.0, 60.0 / max(a.steps, 1)), m) for _ in range(a.steps)]
+    vals = [cpu_baseline(max(4.0, 60.0 / max(a.steps, 1)), m, ref) for _ in range(a.steps)]
     dt = time.perf_counter() - t0
     v = sum(x["value"] for x in vals) / len(vals)
     cb = dict(vals[-1]); cb["value"] = round(v, 3)
     return {"impl": "reference", "metric": "stage1_tok_per_s", "value": round(v, 3), "unit": "tokens/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(dt / a.steps * 1e3, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1] stage-1 (each step = a bounded sample of the 750-token utterance: prefill T=48 + decode steps for a fixed time budget)"},
+            "config": {"workload": "BASELINE configs[1] stage-1 (each step = a bounded sample of the 750-token utterance: prefill T=48 + decode steps sized to a fixed time budget)"},
             "cpu_baseline": cb, "e2e": {"value": round(v, 3), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
 

@@ -1,49 +1,97 @@
-// Path C: ONE persistent kernel per decode position (fast_model.py:150-163 for S = 1), all 24 layers.
+// Path C: ONE persistent kernel for a whole burst of decode positions (fast_model.py:150-163 for S = 1, all 24
+// layers, + the sampler and loop bookkeeping of fast_inference_utils.py:61-120, 148-174): the kernel stays resident
+// across tokens -- no launch, no host round trip and no cold start between positions.
 //
 //   * grid = one CTA per SM; every CTA owns a static slice of every weight matrix:
 //       (K split s = cta % S, row tiles t = cta / S, + groups, ...)  chosen per matrix on the host.
-//   * warp 0 = PRODUCER: one thread walks the whole step's byte schedule -- weight tiles via TMA
-//     (cp.async.bulk.tensor, 128B swizzle) into a ring of 16 KB smem stages, KV-cache tiles via cp.async.bulk
-//     into two dedicated (K,V) tile slots -- all guarded by full/empty mbarriers.  Weights and old KV do not
-//     depend on this step's activations, so the producer never waits for a grid barrier: the HBM stream keeps
-//     running across phase boundaries, and a layer's first KV tiles are in flight before its QKV GEMM starts.
-//   * warp 1 = MMA ISSUER: one thread issues tcgen05.mma (M=128 weight rows x N activation columns, fp32
-//     accumulators double-buffered in TMEM) straight from the ring; activations are the exact hi+lo bf16
-//     split of the fp32 vectors (N = 16: 8 rows, N = 32: 16 rows), so products match fp32-activation math to ~1e-5.
-//   * warps 2..5 = COMPUTE: wait for the previous phase grid-wide (split arrive/wait counter with
-//     release/acquire atomics), stage the B operand into swizzled smem (RMSNorm / attention-merge / SiLU*mul
-//     fused here), run the epilogues (tcgen05.ld -> red.global.add.f32 split-K accumulation) and the decode
-//     attention on smem KV tiles (online softmax per half-warp).
-//   * phases per layer: QKV | attention (+KV-cache append) | wo+residual | w1,w3 | w2+residual, then head.
-//     5 grid-wide dependencies per layer, no host involvement, no per-layer launch.
+//   * warp 0 = PRODUCER: walks the whole burst's byte schedule -- weight tiles via TMA (cp.async.bulk.tensor, 128B
+//     swizzle) into a ring of smem stages, KV-cache tiles via cp.async.bulk into two dedicated (K,V) tile slots -- all
+//     guarded by full/empty mbarriers.  Weights do not depend on activations, so the producer never waits for a grid
+//     barrier: the HBM stream keeps running across phase, layer AND token boundaries (the next token's first weight
+//     tiles land while the grid is still sampling).
+//   * warp 1 = MMA ISSUER (tcgen05.mma, fp32 accumulators double-buffered in TMEM).  Two operand assignments:
+//       WB = true : the streamed weight tile [256 rows x 64 k] is the UMMA *B* operand (N = 256), the staged activation
+//                   rows (hi + lo bf16 halves, <= 32 rows) the *A* operand (M = 128; rows past NB read whatever follows in
+//                   shared memory, their accumulator lanes are never looked at).  An SS-mode UMMA fetches A at one row
+//                   per cycle, so an instruction costs ~130-150 cycles whether it multiplies 16 or 256 weight rows:
+//                   8 KB of weights per instruction.
+//       WB = false: weight tile [128 x 64] as the A operand (M = 128), activations as B (N = NB): 4 KB per instruction
+//                   (round-1 formulation, kept selectable for A/B measurements).
+//   * warps 2..5 = COMPUTE: wait for the previous phase grid-wide (split arrive/wait counter with release/acquire
+//     atomics), stage the activation operand into swizzled smem (RMSNorm gain / attention-merge / SiLU*mul fused
+//     here), run the epilogues (tcgen05.ld -> red.global.add.f32 split-K accumulation), the decode attention on smem
+//     KV tiles (online softmax per half-warp) and the grid-distributed sampler.
+//   * warp 6 = optional L2 PREFETCHER: keeps a window of the flat weight-tile schedule in flight with
+//     cp.async.bulk.prefetch.tensor so that HBM keeps streaming while the grid synchronises.
+//   * RMSNorm statistic without a full-row re-read: every CTA stages x[k-slice] * gain; the CTAs of tile group 0 add
+//     their slice's sum of squares into stat[norm][row] (one red.add per row); the CONSUMER of the projection applies
+//     rsqrt(stat / D + eps): attention scales q, k, v; the w2 staging scales g, u; the sampler scales the logits.
+//     (x W^T) * rs == (x * rs) W^T up to fp32 rounding order.
+//   * phases per layer: QKV | attention (+KV-cache append) | wo+residual | w1,w3 | w2+residual, then head, then
+//     (fused mode) the sampler: every CTA ranks its own ~18 vocabulary entries against all 2562 (no sort), two more
+//     grid barriers combine the kept mass and the exp-race arg-max, the utterance's owner CTA does the bookkeeping and
+//     embeds the next token.
 #pragma once
 #include "stage1_kernels.cuh"
 #include "umma.cuh"
 
 namespace mvb {
 
-constexpr int PC_THREADS = 224;      // producer warp + MMA warp + 4 compute warps + second producer warp
-constexpr int PC_STAGE_BYTES = 16384;
+constexpr int PC_THREADS = 224;      // producer warp + MMA warp + 4 compute warps + L2 prefetch warp
+constexpr int PC_KV_TILE_BYTES = 16384;   // K (or V) tile of one (row, head): 64 bf16 / 32 fp32 positions
 constexpr int PC_RPAD = 16;          // rows of the fp32 activation buffers (8 utterances x 2 CFG rows)
-constexpr int PC_BKB_MAX = 12;       // k-blocks of B one CTA may own in a phase
+constexpr int PC_BKB_MAX = 12;       // k-blocks of the activation operand one CTA may own in a phase
 constexpr int PC_NKV = 2;            // (K tile, V tile) slots
 constexpr int PC_MAX_CHUNKS = 64;    // per (row, head): ceil(2048 / 32) in fp32 mode
 constexpr int PC_TRACE_EVENTS = 512;
 constexpr int PC_MAX_TILES = 128;    // attention KV tiles one CTA may own per layer
+constexpr int PC_SAMP_OWN = 32;      // vocabulary entries one CTA may own in the fused sampler (ceil(V / grid))
 
-template <int NB> struct PcCfg {
-  static constexpr int STAGES = (NB == 16) ? 8 : 6;
+struct AttTile {
+  uint32_t off;     // byte offset of the tile inside one layer's K (or V) region
+  uint32_t meta;    // npos | has_cur << 8 | unit_first << 9 | unit_last << 10 | owns_cur << 11
+  uint32_t where;   // r | h << 8 | z << 16 | cache_row << 24
+  int L;            // positions of the row incl. the current token
+};
+
+struct PcShared {   // small shared state behind the big buffers
+  uint64_t b_full[8], b_empty[8], b_ready, acc_full[2], acc_empty[2], kv_full[PC_NKV], kv_empty[PC_NKV], tab_ready;
+  uint32_t tmem_slot;
+  int prod_pos;                      // weight tiles issued so far (producer -> L2 prefetcher)
+  int n_att_tiles;
+  // every CTA's private copy of the decode state of the batch (kept in lock-step: the same deterministic update
+  // from the same arg-max in every CTA; only the owner CTA writes it back to global memory)
+  int st_pos[PC_RPAD / 2], st_ngen[PC_RPAD / 2], st_done[PC_RPAD / 2], st_tok[PC_RPAD];
+  // per-utterance constants of the launch (read once: every later use would cost a dependent global round trip)
+  SamplingDev c_samp[PC_RPAD / 2];
+  const float* c_noise[PC_RPAD / 2];
+  const int* c_forced[PC_RPAD / 2];
+  int c_budget[PC_RPAD / 2], c_nbase[PC_RPAD / 2], c_slot[PC_RPAD / 2];
+  float o[8 * 128];                  // attention: per-half-warp partial outputs
+  float m[8], l[8];
+  float cur[256];                    // k, v of the current token
+  float ss[PC_RPAD];                 // sum of squares of this CTA's K slice, per row
+  float red[8];                      // block reductions (sampler)
+  unsigned long long best[4];
+  float own_ke[PC_RPAD / 2][PC_SAMP_OWN];   // sampler: kept exp-values of this CTA's vocabulary entries, per utterance
+  int row_nz[PC_RPAD];
+  AttTile att_tab[PC_MAX_TILES];
+};
+
+template <int NB, bool WB> struct PcCfg {
+  static constexpr int TILE_ROWS = WB ? 256 : 128;
+  static constexpr int STAGE_BYTES = TILE_ROWS * 128;     // [TILE_ROWS x 64 k] bf16
+  static constexpr int STAGES = WB ? ((NB == 16) ? 4 : 3) : ((NB == 16) ? 8 : 6);
   static constexpr int B_BYTES = PC_BKB_MAX * NB * 128;
-  static constexpr int RH = NB / 2;                      // activation rows carried (hi rows; lo rows follow)
-  static constexpr int TMEM_COLS = 256;   // 2 accumulators (2 NB columns) + 4 weight-tile A buffers of 32 columns (A-in-TMEM mode)
-  static constexpr int A_COL0 = 2 * NB;
-  static constexpr size_t SMEM = 1024 + (size_t)STAGES * PC_STAGE_BYTES + B_BYTES + (size_t)PC_NKV * 2 * PC_STAGE_BYTES +
-                                 (2 * STAGES + 1 + 4 + 2 * PC_NKV + 1) * 8 + 16 + (1024 + 8 + 8 + PC_RPAD + 256 + 64) * 4 +
-                                 PC_MAX_TILES * 16 + (PC_RPAD + 4) * 4 + 64;
+  static constexpr int RH = NB / 2;                       // activation rows carried (hi rows; lo rows follow)
+  static constexpr int ACC_COLS = WB ? 256 : NB;          // TMEM columns of one accumulator
+  static constexpr int TMEM_COLS = WB ? 512 : 64;
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + B_BYTES + (size_t)PC_NKV * 2 * PC_KV_TILE_BYTES +
+                                 sizeof(PcShared) + 64;
 };
 
 struct PcMat {     // one weight matrix kind, static decomposition
-  int T;           // row tiles (of 128)
+  int T;           // row tiles (of TILE_ROWS)
   int KB;          // k-blocks (of 64)
   int S;           // K splits
   int G;           // tile groups = gridDim / S
@@ -51,9 +99,11 @@ struct PcMat {     // one weight matrix kind, static decomposition
 
 struct PcParams {
   int n_layer, D, F, V, H, S_max, R, n_utts, kv_fp32;
-  int n_prod;      // TMA producer threads (1 or 2): one issuing thread tops out at ~64 GB/s per SM (tools/micro/tma_bench)
-  int ts;          // 1: copy each weight tile smem -> TMEM (tcgen05.cp) and run the UMMAs with A in tensor memory
-  int pf_ahead;    // weight tiles prefetched into L2 ahead of the smem ring (0 = off)
+  int n_steps;     // decode positions this launch runs
+  int fused;       // 1: sample in the kernel and advance the decode state (top_k == 0 only); 0: leave normalised logits
+  int pf_mode;     // 0: no L2 prefetch, 1: by the producer while the ring is full, 2: dedicated prefetch warp
+  int pf_ahead;    // weight tiles prefetched into L2 ahead of the smem ring
+  int epi_mode;    // WB epilogue: 0 = 32x32b loads + red.v4, 1 = 32x32b loads + scalar red, 2 = 16x256b fragment loads + scalar red
   float eps;
   PcMat m_qkv, m_o, m_w13, m_w2, m_head;
   const __nv_bfloat16* attn_norm;   // layer 0; layer l at + l * layer_stride
@@ -66,9 +116,12 @@ struct PcParams {
   float* x;        // [RPAD, D]   residual stream (red.add target of wo / w2)
   float* qkv;      // [RPAD, 3D]  red.add target, zeroed during the wo phase
   float* gu;       // [RPAD, 2F]  g | u, red.add target, zeroed during the attention phase
-  float* logits;   // [2*max_utts, V] sampler buffer (zeroed by the sampler after use)
+  float* logits;   // [2*max_utts, V] red.add target (zero at launch; re-zeroed by the fused sampler)
   float* part_o;   // [RPAD*H*PC_MAX_CHUNKS, 128]
   float* part_ml;  // [RPAD*H*PC_MAX_CHUNKS, 2]
+  float* stat;     // [2*n_layer + 1][RPAD] sums of squares of the normalised rows (attn, ffn per layer; final)
+  float* samp_part;               // [RPAD/2][gridDim] kept probability mass of every CTA's vocabulary entries
+  unsigned long long* samp_best;  // [2][RPAD/2] exp-race arg-max candidates (double-buffered by step parity)
   char* kv;
   size_t kv_half;  // bytes of one layer's K (or V) region
   unsigned* bar;   // grid-wide arrival counter (zero at launch)
@@ -87,6 +140,9 @@ __device__ __forceinline__ void red_release_inc(unsigned* p) {
 }
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -97,13 +153,43 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
       ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
 }
-
 // Pull a weight tile into L2 only (no smem, no barrier): HBM keeps streaming while the ring is full.
 __device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// 32 lanes x 64 consecutive 32-bit columns of tensor memory
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+      "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]),
+        "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]),
+        "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]),
+        "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
+}
 
-// byte offset of the 16-byte chunk holding k..k+7 of activation row `row` inside the B operand
+// 16 lanes x 64 consecutive 32-bit columns, fragment layout (PTX tcgen05.ld .16x256b; cute SM100_TMEM_LOAD_16dp256b8x):
+// thread T holds, for repetition i = 0..7, r[4i+0..1] = (lane T/4, columns 8i + 2(T%4) + {0,1}) and
+// r[4i+2..3] = (lane T/4 + 8, same columns).  All 32 threads carry data as soon as 8 rows are live.
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// byte offset of the 16-byte chunk holding k..k+7 of activation row `row` inside the activation operand
 // (K-major, 128B swizzle, [k-block][NB rows][128 B])
 template <int NB>
 __device__ __forceinline__ uint32_t b_chunk_off(int kb_local, int row, int kchunk /* (k % 64) / 8 */) {
@@ -156,20 +242,14 @@ __device__ __forceinline__ AttSplit att_split(int L, int ppc, int zmax) {
   return a;
 }
 // Per-step attention tile table of this CTA (identical for every layer; only the layer base pointer differs):
-// built once by one thread, walked by the producer (KV loads) and by the compute warps.
-struct AttTile {
-  uint32_t off;     // byte offset of the tile inside one layer's K (or V) region
-  uint32_t meta;    // npos | has_cur << 8 | unit_first << 9 | unit_last << 10 | owns_cur << 11
-  uint32_t where;   // r | h << 8 | z << 16 | cache_row << 24
-  int L;            // positions of the row incl. the current token
-};
-__device__ __forceinline__ int build_att_table(const PcParams& p, int cta, int G, int ppc, int esz, AttTile* tab, int* row_nz) {
+// built once per token by one thread, walked by the producer (KV loads) and by the compute warps.
+__device__ __forceinline__ int build_att_table(const PcParams& p, const int* st_pos, const int* c_slot, int cta, int G, int ppc, int esz, AttTile* tab, int* row_nz) {
   const int zmax = max(1, G / (p.R * p.H));
   int nt = 0, base = 0;
   int id = cta;
   for (int r = 0; r < p.R; ++r) {
-    const int u = p.st.slot_map[r >> 1];
-    const int L = p.st.pos[u] + 1;
+    const int u = c_slot[r >> 1];
+    const int L = min(st_pos[r >> 1], p.S_max - 1) + 1;   // the decode state keeps pos inside the cache; clamp anyway
     const AttSplit a = att_split(L, ppc, zmax);
     row_nz[r] = a.nz;
     const int units = p.H * a.nz;
@@ -210,113 +290,119 @@ __device__ __forceinline__ void load8s(const uint8_t* tile, int p, int sub, floa
   }
 }
 
-template <bool KV_FP32, int NB>
+template <bool KV_FP32, int NB, bool WB>
 __global__ void __launch_bounds__(PC_THREADS, 1)
 k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_o,
                     const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w3,
                     const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_head,
                     const PcParams p) {
-  using Cfg = PcCfg<NB>;
+  using Cfg = PcCfg<NB, WB>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int RH = Cfg::RH;
+  constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int TILE_ROWS = Cfg::TILE_ROWS;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by POINTER ARITHMETIC on the shared array: an integer round trip would lose the .shared state
+  // space and turn every access below into a generic LD/ST (higher latency, no LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem;
-  uint8_t* Bop = ring + STAGES * PC_STAGE_BYTES;
-  uint8_t* kvbuf = Bop + Cfg::B_BYTES;                       // [NKV][K tile | V tile]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kvbuf + PC_NKV * 2 * PC_STAGE_BYTES);
-  uint64_t* b_full = bars;
-  uint64_t* b_empty = b_full + STAGES;
-  uint64_t* b_ready = b_empty + STAGES;
-  uint64_t* acc_full = b_ready + 1;
-  uint64_t* acc_empty = acc_full + 2;
-  uint64_t* kv_full = acc_empty + 2;
-  uint64_t* kv_empty = kv_full + PC_NKV;
-  uint64_t* tab_ready = kv_empty + PC_NKV;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tab_ready + 1);
-  float* sm_f = reinterpret_cast<float*>(tmem_slot + 4);
-  AttTile* att_tab = reinterpret_cast<AttTile*>(sm_f + (1024 + 8 + 8 + PC_RPAD + 256 + 64));
-  int* row_nz = reinterpret_cast<int*>(att_tab + PC_MAX_TILES);   // [PC_RPAD] splits per row, then [1] tile count
+  uint8_t* Bop = ring + STAGES * STAGE_BYTES;
+  uint8_t* kvbuf = Bop + Cfg::B_BYTES;                       // [NKV][K tile | V tile]; sampler scratch between tokens
+  PcShared& sh = *reinterpret_cast<PcShared*>(kvbuf + PC_NKV * 2 * PC_KV_TILE_BYTES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x, G = gridDim.x;
   const int esz = KV_FP32 ? 4 : 2;
-  const int ppc = PC_STAGE_BYTES / (128 * esz);             // positions per KV tile
+  const int ppc = PC_KV_TILE_BYTES / (128 * esz);             // positions per KV tile
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(ptx::smem_u32(b_full + s), 1);
-      ptx::mbar_init(ptx::smem_u32(b_empty + s), 1);
+      ptx::mbar_init(ptx::smem_u32(sh.b_full + s), 1);
+      ptx::mbar_init(ptx::smem_u32(sh.b_empty + s), 1);
     }
-    ptx::mbar_init(ptx::smem_u32(b_ready), 1);
+    ptx::mbar_init(ptx::smem_u32(&sh.b_ready), 1);
     for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(ptx::smem_u32(acc_full + i), 1);
-      ptx::mbar_init(ptx::smem_u32(acc_empty + i), 128);
+      ptx::mbar_init(ptx::smem_u32(sh.acc_full + i), 1);
+      ptx::mbar_init(ptx::smem_u32(sh.acc_empty + i), WB ? 1 : 128);   // WB: one arrive by the TMEM-reading warp
     }
     for (int i = 0; i < PC_NKV; ++i) {
-      ptx::mbar_init(ptx::smem_u32(kv_full + i), 1);
-      ptx::mbar_init(ptx::smem_u32(kv_empty + i), 1);
+      ptx::mbar_init(ptx::smem_u32(sh.kv_full + i), 1);
+      ptx::mbar_init(ptx::smem_u32(sh.kv_empty + i), 1);
     }
-    ptx::mbar_init(ptx::smem_u32(tab_ready), 1);
+    ptx::mbar_init(ptx::smem_u32(&sh.tab_ready), 1);
+    sh.prod_pos = 0;
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(ptx::smem_u32(tmem_slot), Cfg::TMEM_COLS);
+    ptx::tmem_alloc(ptx::smem_u32(&sh.tmem_slot), Cfg::TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  // zero the B operand once: rows >= R (hi and lo halves) must read as zero forever
+  // zero the activation operand once: rows >= R (hi and lo halves) must read as zero forever
   for (int i = tid; i < Cfg::B_BYTES / 16; i += PC_THREADS) reinterpret_cast<uint4*>(Bop)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < PC_RPAD) sh.ss[tid] = 0.f;
   fence_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // provably warp-uniform (no operand waterfall at the tcgen05 sites)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, sh.tmem_slot, 0);   // provably warp-uniform (no operand waterfall at the tcgen05 sites)
   pdl_launch_dependents();
 
   const PcSlice s_qkv = pc_slice(p.m_qkv, cta), s_o = pc_slice(p.m_o, cta), s_w13 = pc_slice(p.m_w13, cta),
                 s_w2 = pc_slice(p.m_w2, cta), s_head = pc_slice(p.m_head, cta);
   const int T1 = p.m_w13.T >> 1;  // w1 tiles; tiles >= T1 belong to w3
+  // Flat view of this CTA's weight-tile schedule of ONE token (layer-major: qkv, wo, w1|w3, w2; then the head)
+  const int nk_q = s_qkv.kb1 - s_qkv.kb0, nk_o = s_o.kb1 - s_o.kb0, nk_f = s_w13.kb1 - s_w13.kb0,
+            nk_2 = s_w2.kb1 - s_w2.kb0, nk_h = s_head.kb1 - s_head.kb0;
+  const int c_q = s_qkv.nt * nk_q, c_o = s_o.nt * nk_o, c_f = s_w13.nt * nk_f, c_2 = s_w2.nt * nk_2;
+  const int per_layer = c_q + c_o + c_f + c_2;
+  const int total_tiles = p.n_layer * per_layer + s_head.nt * nk_h;
 
   if (warp == 0 || warp == 6) {
-    // =================================== PRODUCER(S) ================================================
-    // Weight tile n of the flat schedule is issued by producer (n % n_prod); producer 0 also feeds the KV slots.
+    // =================================== PRODUCER / L2 PREFETCHER ===================================
     // The whole warp walks the schedule (warp-uniform control flow and operands); one elected lane issues the TMA /
     // bulk-copy instructions.  Issuing them from a `lane == 0` branch makes the compiler wrap each UTMALDG in an
     // ELECT + 4 x R2UR.BROADCAST + vote loop, which capped one producer at a tile per ~0.25 us.
-    const int pid = warp == 0 ? 0 : 1;
-    const int NPROD = p.n_prod;
-    if (pid < NPROD) {
-      const uint64_t pol = ptx::policy_evict_first();
-      uint32_t slot = 0, kv_ctr = 0;
-      // Flat view of this CTA's weight-tile schedule (layer-major: qkv, wo, w1|w3, w2; then the head), used by the
-      // L2 prefetch cursor that runs `pf_ahead` tiles in front of the smem ring.
-      const int nk_q = s_qkv.kb1 - s_qkv.kb0, nk_o = s_o.kb1 - s_o.kb0, nk_f = s_w13.kb1 - s_w13.kb0,
-                nk_2 = s_w2.kb1 - s_w2.kb0, nk_h = s_head.kb1 - s_head.kb0;
-      const int c_q = s_qkv.nt * nk_q, c_o = s_o.nt * nk_o, c_f = s_w13.nt * nk_f, c_2 = s_w2.nt * nk_2;
-      const int per_layer = c_q + c_o + c_f + c_2;
-      const int total_tiles = p.n_layer * per_layer + s_head.nt * nk_h;
-      auto prefetch_flat = [&](int n) {
-        if (n >= total_tiles) return;
-        const CUtensorMap* tm;
-        const PcSlice* sl;
-        int nk, layer = 0, m;
-        if (n >= p.n_layer * per_layer) {
-          m = n - p.n_layer * per_layer; tm = &tm_head; sl = &s_head; nk = nk_h;
-        } else {
-          layer = n / per_layer;
-          m = n - layer * per_layer;
-          if (m < c_q) { tm = &tm_qkv; sl = &s_qkv; nk = nk_q; }
-          else if (m < c_q + c_o) { m -= c_q; tm = &tm_o; sl = &s_o; nk = nk_o; }
-          else if (m < c_q + c_o + c_f) { m -= c_q + c_o; tm = &tm_w1; sl = &s_w13; nk = nk_f; }
-          else { m -= c_q + c_o + c_f; tm = &tm_w2; sl = &s_w2; nk = nk_2; }
+    auto prefetch_flat = [&](int n) {      // n: index inside one token's schedule
+      const CUtensorMap* tm;
+      const PcSlice* sl;
+      int nk, layer = 0, m;
+      if (n >= p.n_layer * per_layer) {
+        m = n - p.n_layer * per_layer; tm = &tm_head; sl = &s_head; nk = nk_h;
+      } else {
+        layer = n / per_layer;
+        m = n - layer * per_layer;
+        if (m < c_q) { tm = &tm_qkv; sl = &s_qkv; nk = nk_q; }
+        else if (m < c_q + c_o) { m -= c_q; tm = &tm_o; sl = &s_o; nk = nk_o; }
+        else if (m < c_q + c_o + c_f) { m -= c_q + c_o; tm = &tm_w1; sl = &s_w13; nk = nk_f; }
+        else { m -= c_q + c_o + c_f; tm = &tm_w2; sl = &s_w2; nk = nk_2; }
+      }
+      const int ti = m / nk, kb = sl->kb0 + (m - ti * nk);
+      int t = sl->t0 + ti * sl->G;
+      if (sl == &s_w13 && t >= T1) { t -= T1; tm = &tm_w3; }
+      if (ptx::elect_one()) tma_prefetch_3d(tm, kb * 64, t * TILE_ROWS, layer);
+      __syncwarp();
+    };
+    const long long total_all = (long long)total_tiles * p.n_steps;
+    if (warp == 6) {
+      if (p.pf_mode == 2 && total_tiles > 0) {
+        // Dedicated L2 prefetcher: keeps the window (issued, issued + pf_ahead] of the flat tile schedule in flight so
+        // that HBM keeps streaming while the grid synchronises; it never touches the smem ring.
+        const uint32_t pp = ptx::smem_u32(&sh.prod_pos);
+        long long n = STAGES;
+        while (n < total_all) {
+          int pos_l;
+          asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(pos_l) : "r"(pp) : "memory");
+          const long long pos = __shfl_sync(0xffffffffu, pos_l, 0);   // one value for the whole warp
+          if (n < pos) n = pos;
+          if (n < pos + p.pf_ahead) { prefetch_flat((int)(n % total_tiles)); ++n; }
+          else __nanosleep(64);
         }
-        const int ti = m / nk, kb = sl->kb0 + (m - ti * nk);
-        int t = sl->t0 + ti * sl->G;
-        if (sl == &s_w13 && t >= T1) { t -= T1; tm = &tm_w3; }
-        if (ptx::elect_one()) tma_prefetch_3d(tm, kb * 64, t * 128, layer);
-        __syncwarp();
-      };
-      int issued = 0, pf_next = 0;   // prefetch only while the ring is full: idle producer time -> HBM keeps streaming into L2
+      }
+    } else {
+      const uint64_t pol = ptx::policy_evict_first();
+      const uint32_t pp = ptx::smem_u32(&sh.prod_pos);
+      uint32_t slot = 0, kv_ctr = 0;
+      long long issued = 0, pf_next = 0;   // inline prefetch (pf_mode 1) only while the ring is full
       auto gemm_tiles = [&](const CUtensorMap* tmA, const CUtensorMap* tmB2, int split_t, const PcSlice& sl, int layer) {
         for (int i = 0; i < sl.nt; ++i) {
           const int t = sl.t0 + i * sl.G;
@@ -325,22 +411,22 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           for (int kb = sl.kb0; kb < sl.kb1; ++kb) {
             const uint32_t s = slot % STAGES, ph = (slot / STAGES) & 1u;
             ++slot;
-            if (NPROD > 1 && (issued % NPROD) != pid) { ++issued; continue; }   // the other producer's tile
-            const uint32_t eb = ptx::smem_u32(b_empty + s);
-            if (p.pf_ahead > 0 && !ptx::mbar_test_wait(eb, ph ^ 1u)) {
+            const uint32_t eb = ptx::smem_u32(sh.b_empty + s);
+            if (p.pf_mode == 1 && !ptx::mbar_test_wait(eb, ph ^ 1u)) {
               // the ring is full: spend the idle time pulling upcoming tiles into L2 (non-blocking probe)
-              if (pf_next <= issued) pf_next = issued + NPROD;      // never prefetch a tile that is about to be loaded
-              while (pf_next < issued + 1 + p.pf_ahead && pf_next < total_tiles && !ptx::mbar_test_wait(eb, ph ^ 1u)) {
-                prefetch_flat(pf_next);
-                pf_next += NPROD;
+              if (pf_next <= issued) pf_next = issued + 1;      // never prefetch a tile that is about to be loaded
+              while (pf_next < issued + 1 + p.pf_ahead && pf_next < total_all && !ptx::mbar_test_wait(eb, ph ^ 1u)) {
+                prefetch_flat((int)(pf_next % total_tiles));
+                ++pf_next;
               }
             }
             ptx::mbar_wait(eb, ph ^ 1u);
             ++issued;
             if (ptx::elect_one()) {
-              const uint32_t full = ptx::smem_u32(b_full + s);
-              ptx::mbar_arrive_expect_tx(full, PC_STAGE_BYTES);
-              tma_load_3d(ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES), tm, full, kb * 64, tt * 128, layer, pol);
+              const uint32_t full = ptx::smem_u32(sh.b_full + s);
+              ptx::mbar_arrive_expect_tx(full, STAGE_BYTES);
+              tma_load_3d(ptx::smem_u32(ring + (size_t)s * STAGE_BYTES), tm, full, kb * 64, tt * TILE_ROWS, layer, pol);
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(pp), "r"((int)issued) : "memory");
             }
             __syncwarp();
           }
@@ -350,10 +436,10 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       auto kv_units = [&](int l, int from, int to) {
         const char* kbase = p.kv + (size_t)l * 2 * p.kv_half;
         const char* vbase = kbase + p.kv_half;
-        const int n_tiles = row_nz[PC_RPAD];
+        const int n_tiles = sh.n_att_tiles;
         int idx = 0;
         for (int i = 0; i < n_tiles; ++i) {
-          const AttTile e = att_tab[i];
+          const AttTile e = sh.att_tab[i];
           const int npos = (int)(e.meta & 0xffu);
           if (npos == 0) continue;                 // only the current position: it comes from registers
           const int my = idx++;
@@ -361,90 +447,78 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           if (my >= to) break;
           const uint32_t ks = kv_ctr % PC_NKV, ph = (kv_ctr / PC_NKV) & 1u;
           ++kv_ctr;
-          ptx::mbar_wait(ptx::smem_u32(kv_empty + ks), ph ^ 1u);
+          ptx::mbar_wait(ptx::smem_u32(sh.kv_empty + ks), ph ^ 1u);
           if (ptx::elect_one()) {
             const uint32_t bytes = (uint32_t)npos * 128 * esz;
-            const uint32_t full = ptx::smem_u32(kv_full + ks);
+            const uint32_t full = ptx::smem_u32(sh.kv_full + ks);
             ptx::mbar_arrive_expect_tx(full, 2 * bytes);
-            uint8_t* dst = kvbuf + (size_t)ks * 2 * PC_STAGE_BYTES;
+            uint8_t* dst = kvbuf + (size_t)ks * 2 * PC_KV_TILE_BYTES;
             bulk_load(ptx::smem_u32(dst), kbase + e.off, bytes, full);
-            bulk_load(ptx::smem_u32(dst + PC_STAGE_BYTES), vbase + e.off, bytes, full);
+            bulk_load(ptx::smem_u32(dst + PC_KV_TILE_BYTES), vbase + e.off, bytes, full);
           }
           __syncwarp();
         }
       };
-      for (int l = 0; l < p.n_layer; ++l) {
-        if (l == 0) {
-          gemm_tiles(&tm_qkv, &tm_qkv, 1 << 30, s_qkv, 0);   // weights first: they need nothing from the previous kernel
-          if (pid == 0) {
-            ptx::mbar_wait(ptx::smem_u32(tab_ready), 0);      // tile table built (after the PDL wait) by the compute warps
+      for (int step = 0; step < p.n_steps; ++step) {
+        for (int l = 0; l < p.n_layer; ++l) {
+          if (l == 0) {
+            gemm_tiles(&tm_qkv, &tm_qkv, 1 << 30, s_qkv, 0);   // weights first: they need nothing from the previous token
+            ptx::mbar_wait(ptx::smem_u32(&sh.tab_ready), step & 1u);   // this token's tile table is built
             kv_units(0, 0, 1 << 30);
+          } else {
+            kv_units(l, PC_NKV, 1 << 30);                       // (units beyond the prefetched ones)
           }
-        } else if (pid == 0) {
-          kv_units(l, PC_NKV, 1 << 30);                       // (units beyond the prefetched ones)
+          gemm_tiles(&tm_o, &tm_o, 1 << 30, s_o, l);
+          gemm_tiles(&tm_w1, &tm_w3, T1, s_w13, l);
+          gemm_tiles(&tm_w2, &tm_w2, 1 << 30, s_w2, l);
+          if (l + 1 < p.n_layer) {
+            kv_units(l + 1, 0, PC_NKV);                         // next layer's first KV tiles ride ahead of its QKV GEMM
+            gemm_tiles(&tm_qkv, &tm_qkv, 1 << 30, s_qkv, l + 1);
+          }
         }
-        gemm_tiles(&tm_o, &tm_o, 1 << 30, s_o, l);
-        gemm_tiles(&tm_w1, &tm_w3, T1, s_w13, l);
-        gemm_tiles(&tm_w2, &tm_w2, 1 << 30, s_w2, l);
-        if (l + 1 < p.n_layer) {
-          if (pid == 0) kv_units(l + 1, 0, PC_NKV);           // next layer's first KV tiles ride ahead of its QKV GEMM
-          gemm_tiles(&tm_qkv, &tm_qkv, 1 << 30, s_qkv, l + 1);
-        }
+        gemm_tiles(&tm_head, &tm_head, 1 << 30, s_head, 0);
       }
-      gemm_tiles(&tm_head, &tm_head, 1 << 30, s_head, 0);
     }
   } else if (warp == 1) {
     // =================================== MMA ISSUER =================================================
     // The WHOLE warp walks the schedule (waits, counters, descriptor arithmetic stay warp-uniform -> uniform
-    // registers) and one elected lane issues the tcgen05 instructions.  Issuing from a `lane == 0` branch makes the
-    // compiler wrap every UTCHMMA in an R2UR / ELECT / vote loop: 175 instead of 134 cycles per instruction
-    // (tools/micro/umma_bench.cu).
-    {
-      const uint32_t idesc = ptx::umma_idesc_bf16(128, NB);
-      uint32_t slot = 0, tile_ctr = 0, bphase = 0, a_ctr = 0;
-      auto gemm_phase = [&](const PcSlice& sl) {
-        if (sl.nt == 0) return;
-        ptx::mbar_wait(ptx::smem_u32(b_ready), bphase & 1u);   // B operand of this phase staged
-        ++bphase;
+    // registers) and one elected lane issues the tcgen05 instructions.
+    const uint32_t idesc = WB ? ptx::umma_idesc_bf16(128, 256) : ptx::umma_idesc_bf16(128, NB);
+    uint32_t slot = 0, tile_ctr = 0, bphase = 0;
+    auto gemm_phase = [&](const PcSlice& sl) {
+      if (sl.nt == 0) return;
+      ptx::mbar_wait(ptx::smem_u32(&sh.b_ready), bphase & 1u);   // activation operand of this phase staged
+      ++bphase;
+      ptx::tc_fence_after();
+      for (int i = 0; i < sl.nt; ++i) {
+        const uint32_t ab = tile_ctr & 1u, aph = (tile_ctr >> 1) & 1u;
+        ptx::mbar_wait(ptx::smem_u32(sh.acc_empty + ab), aph ^ 1u);   // epilogue drained this accumulator
         ptx::tc_fence_after();
-        for (int i = 0; i < sl.nt; ++i) {
-          const uint32_t ab = tile_ctr & 1u, aph = (tile_ctr >> 1) & 1u;
-          ptx::mbar_wait(ptx::smem_u32(acc_empty + ab), aph ^ 1u);   // epilogue drained this accumulator
+        const uint32_t dcol = tmem_base + ab * Cfg::ACC_COLS;
+        for (int kb = sl.kb0; kb < sl.kb1; ++kb) {
+          const uint32_t s = slot % STAGES, ph = (slot / STAGES) & 1u;
+          ++slot;
+          ptx::mbar_wait(ptx::smem_u32(sh.b_full + s), ph);
           ptx::tc_fence_after();
-          const uint32_t dcol = tmem_base + ab * NB;
-          for (int kb = sl.kb0; kb < sl.kb1; ++kb) {
-            const uint32_t s = slot % STAGES, ph = (slot / STAGES) & 1u;
-            ++slot;
-            ptx::mbar_wait(ptx::smem_u32(b_full + s), ph);
-            ptx::tc_fence_after();
-            const uint32_t a_addr = ptx::smem_u32(ring + (size_t)s * PC_STAGE_BYTES);
-            const uint64_t ad = ptx::umma_desc_k_sw128(a_addr);
-            const uint64_t bd = ptx::umma_desc_k_sw128(ptx::smem_u32(Bop + (size_t)(kb - sl.kb0) * (NB * 128)));
-            const uint32_t first = (uint32_t)(kb != sl.kb0);
-            if (p.ts) {
-              // Experimental (MVB_PC_TS=1, parity-tested, not faster): copy the tile to tensor memory with tcgen05.cp,
-              // release the smem stage once the copy is done, run the UMMAs with A in TMEM.
-              const uint32_t abuf = tmem_base + Cfg::A_COL0 + (a_ctr & 3u) * 32;
-              ++a_ctr;
-              if (ptx::elect_one()) {
+          const uint64_t wd = ptx::umma_desc_k_sw128(ptx::smem_u32(ring + (size_t)s * STAGE_BYTES));
+          const uint64_t xd = ptx::umma_desc_k_sw128(ptx::smem_u32(Bop + (size_t)(kb - sl.kb0) * (NB * 128)));
+          const uint32_t first = (uint32_t)(kb != sl.kb0);
+          if (ptx::elect_one()) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ptx::tmem_cp_128x256b(abuf + 8 * k, ad + 2 * k);
-                ptx::umma_commit(ptx::smem_u32(b_empty + s));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) ptx::umma_bf16_ts(dcol, abuf + 8 * k, bd + 2 * k, idesc, first | (uint32_t)(k != 0));
-              }
-            } else if (ptx::elect_one()) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) ptx::umma_bf16(dcol, ad + 2 * k, bd + 2 * k, idesc, first | (uint32_t)(k != 0));
-              ptx::umma_commit(ptx::smem_u32(b_empty + s));
+            for (int k = 0; k < 4; ++k) {
+              if (WB) ptx::umma_bf16(dcol, xd + 2 * k, wd + 2 * k, idesc, first | (uint32_t)(k != 0));
+              else ptx::umma_bf16(dcol, wd + 2 * k, xd + 2 * k, idesc, first | (uint32_t)(k != 0));
             }
-            __syncwarp();
+            ptx::umma_commit(ptx::smem_u32(sh.b_empty + s));
           }
-          if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(acc_full + ab));
           __syncwarp();
-          ++tile_ctr;
         }
-      };
+        if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(sh.acc_full + ab));
+        __syncwarp();
+        ++tile_ctr;
+      }
+    };
+    for (int step = 0; step < p.n_steps; ++step) {
       for (int l = 0; l < p.n_layer; ++l) {
         gemm_phase(s_qkv);
         gemm_phase(s_o);
@@ -458,25 +532,14 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     const int ct = tid - 64;            // 0..127
     const int cw = ct >> 5;             // 0..3
     const int quad = warp & 3;          // TMEM lane quadrant this warp may read
-    float* sm_o = sm_f;                 // [8][128]
-    float* sm_m = sm_f + 1024;          // [8]
-    float* sm_l = sm_m + 8;             // [8]
-    float* sm_rs = sm_l + 8;            // [PC_RPAD]
-    float* sm_cur = sm_rs + PC_RPAD;    // [2][128] k, v of the current token
-    float* sm_red = sm_cur + 256;       // [PC_RPAD][4] partial sums of squares
     uint32_t tile_ctr = 0, bar_idx = 0, kv_ctr = 0;
+    const float inv_D = 1.f / (float)p.D;
     pdl_wait();                         // state / x inputs of the previous kernels are visible
-    if (ct == 0) {
-      row_nz[PC_RPAD] = build_att_table(p, cta, G, ppc, esz, att_tab, row_nz);
-      ptx::mbar_arrive(ptx::smem_u32(tab_ready));   // release: the producer may walk the table
-    }
-    compute_sync();
     int ev = 0;
     auto stamp = [&]() {
       if (p.trace != nullptr && ct == 0 && ev < PC_TRACE_EVENTS) p.trace[(size_t)cta * PC_TRACE_EVENTS + ev] = clock64();
       ++ev;
     };
-    stamp();
 
     auto grid_arrive = [&]() {          // bar.sync orders every compute thread's writes before the release
       compute_sync();
@@ -496,67 +559,34 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     auto b_publish = [&]() {            // generic-proxy smem writes -> visible to the tensor core
       fence_async_smem();
       compute_sync();
-      if (ct == 0) ptx::mbar_arrive(ptx::smem_u32(b_ready));
+      if (ct == 0) ptx::mbar_arrive(ptx::smem_u32(&sh.b_ready));
     };
-    // B <- hi/lo split of (x * rstd) * gain over this CTA's K range; RMSNorm statistics (fast_model.py:254-255)
-    // and the chunk loads are issued together so the phase costs ONE L2 round trip.
-    auto stage_norm = [&](const PcSlice& sl, const __nv_bfloat16* gain) {
+    // deterministic block reductions over the 128 compute threads (sampler)
+    auto block_sum = [&](float v) -> float {
+      v = warp_sum(v);
+      if (lane == 0) sh.red[cw] = v;
+      compute_sync();
+      const float r = (sh.red[0] + sh.red[1]) + (sh.red[2] + sh.red[3]);
+      compute_sync();
+      return r;
+    };
+    auto block_max = [&](float v) -> float {
+      v = warp_max(v);
+      if (lane == 0) sh.red[cw] = v;
+      compute_sync();
+      const float r = fmaxf(fmaxf(sh.red[0], sh.red[1]), fmaxf(sh.red[2], sh.red[3]));
+      compute_sync();
+      return r;
+    };
+    // Activation operand <- hi/lo split of x * gain over this CTA's K range (the RMSNorm scale is applied by the
+    // consumer of the projection).  The CTAs of tile group 0 (one per K split) add the slice's sum of squares to stat.
+    auto stage_norm = [&](const PcSlice& sl, const __nv_bfloat16* gain, float* stat_row, bool owns_stat, bool from_emb) {
       if (sl.nt == 0) return;
       const int nchunk = (sl.kb1 - sl.kb0) * 8;
       const int total = p.R * nchunk;
-      constexpr int MAXC = 2;             // chunks pre-loaded per thread (covers R = 2 completely: 176 chunks)
-      float4 ca[MAXC], cb[MAXC];
-      uint4 cg[MAXC];
-#pragma unroll
-      for (int j = 0; j < MAXC; ++j) {
-        const int i = ct + j * 128;
-        if (i < total) {
-          const int n = i / nchunk, c = i - n * nchunk;
-          const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)n * p.D + sl.kb0 * 64 + c * 8);
-          ca[j] = __ldcg(xr);
-          cb[j] = __ldcg(xr + 1);
-          cg[j] = *reinterpret_cast<const uint4*>(gain + sl.kb0 * 64 + c * 8);
-        }
-      }
-      const int f4_per_row = p.D >> 2;
-      for (int n0 = 0; n0 < p.R; n0 += 4) {
-        float ss[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int n = n0 + q;
-          if (n < p.R) {
-            const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)n * p.D);
-            for (int i = ct; i < f4_per_row; i += 128) {
-              const float4 v = __ldcg(xr + i);
-              ss[q] = fmaf(v.x, v.x, ss[q]); ss[q] = fmaf(v.y, v.y, ss[q]);
-              ss[q] = fmaf(v.z, v.z, ss[q]); ss[q] = fmaf(v.w, v.w, ss[q]);
-            }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float s = warp_sum(ss[q]);
-          if (lane == 0 && n0 + q < p.R) sm_red[(n0 + q) * 4 + cw] = s;
-        }
-      }
-      compute_sync();
-      if (ct < p.R) {
-        const float t = sm_red[ct * 4] + sm_red[ct * 4 + 1] + sm_red[ct * 4 + 2] + sm_red[ct * 4 + 3];
-        sm_rs[ct] = rsqrtf(t / (float)p.D + p.eps);
-      }
-      compute_sync();
-      auto emit = [&](int i, const float4& a, const float4& b, const uint4& gw) {
-        const int n = i / nchunk, c = i - n * nchunk;
-        const float rs = sm_rs[n];
-        float v[8] = {(a.x * rs) * bf_lo(gw.x), (a.y * rs) * bf_hi(gw.x), (a.z * rs) * bf_lo(gw.y), (a.w * rs) * bf_hi(gw.y),
-                      (b.x * rs) * bf_lo(gw.z), (b.y * rs) * bf_hi(gw.z), (b.z * rs) * bf_lo(gw.w), (b.w * rs) * bf_hi(gw.w)};
-        b_store8<NB>(Bop, c >> 3, n, c & 7, v);
-      };
-#pragma unroll
-      for (int j = 0; j < MAXC; ++j)
-        if (ct + j * 128 < total) emit(ct + j * 128, ca[j], cb[j], cg[j]);
-      // larger batches: 2 chunks (6 loads) in flight per thread per trip
-      for (int i0 = ct + MAXC * 128; i0 < total; i0 += 2 * 128) {
+      // 2 chunks (6 loads) in flight per thread per trip; the trip count is warp-uniform (the statistic uses warp votes)
+      for (int base = cw * 32; base < total; base += 2 * 128) {
+        const int i0 = base + lane;
         float4 la[2], lb[2];
         uint4 lg[2];
 #pragma unroll
@@ -564,17 +594,67 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           const int i = i0 + j * 128;
           if (i < total) {
             const int n = i / nchunk, c = i - n * nchunk;
-            const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)n * p.D + sl.kb0 * 64 + c * 8);
-            la[j] = __ldcg(xr);
-            lb[j] = __ldcg(xr + 1);
-            lg[j] = *reinterpret_cast<const uint4*>(gain + sl.kb0 * 64 + c * 8);
+            const int k = sl.kb0 * 64 + c * 8;
+            lg[j] = *reinterpret_cast<const uint4*>(gain + k);
+            if (!from_emb) {
+              const float4* xr = reinterpret_cast<const float4*>(p.x + (size_t)n * p.D + k);
+              la[j] = __ldcg(xr);
+              lb[j] = __ldcg(xr + 1);
+            } else {
+              // first layer of a token: x = tok_emb + pos_emb (+ speaker projection on the conditioned row) straight from
+              // the tables (fast_model.py:152-157) -- no grid-wide wait for the owner CTA's x rows
+              const int b = n >> 1;
+              const uint4 wt = *reinterpret_cast<const uint4*>(p.tok_emb + (size_t)sh.st_tok[n] * p.D + k);
+              const uint4 wp = *reinterpret_cast<const uint4*>(p.pos_emb + (size_t)min(sh.st_pos[b], p.S_max - 1) * p.D + k);
+              float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+              if ((n & 1) == 0) {
+                const float* sp = p.spk_proj + (size_t)sh.c_slot[b] * p.D + k;
+                sa = *reinterpret_cast<const float4*>(sp);
+                sb = *reinterpret_cast<const float4*>(sp + 4);
+              }
+              la[j] = make_float4((bf_lo(wt.x) + bf_lo(wp.x)) + sa.x, (bf_hi(wt.x) + bf_hi(wp.x)) + sa.y,
+                                  (bf_lo(wt.y) + bf_lo(wp.y)) + sa.z, (bf_hi(wt.y) + bf_hi(wp.y)) + sa.w);
+              lb[j] = make_float4((bf_lo(wt.z) + bf_lo(wp.z)) + sb.x, (bf_hi(wt.z) + bf_hi(wp.z)) + sb.y,
+                                  (bf_lo(wt.w) + bf_lo(wp.w)) + sb.z, (bf_hi(wt.w) + bf_hi(wp.w)) + sb.w);
+            }
           }
         }
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-          if (i0 + j * 128 < total) emit(i0 + j * 128, la[j], lb[j], lg[j]);
+        for (int j = 0; j < 2; ++j) {
+          const int i = i0 + j * 128;
+          const bool act = i < total;                  // (trip counts are warp-uniform except in the last warp-trip)
+          int n = 0, c = 0;
+          float sq = 0.f;
+          if (act) {
+            n = i / nchunk; c = i - n * nchunk;
+            const float4 a = la[j], b = lb[j];
+            const uint4 gw = lg[j];
+            float v[8] = {a.x * bf_lo(gw.x), a.y * bf_hi(gw.x), a.z * bf_lo(gw.y), a.w * bf_hi(gw.y),
+                          b.x * bf_lo(gw.z), b.y * bf_hi(gw.z), b.z * bf_lo(gw.w), b.w * bf_hi(gw.w)};
+            b_store8<NB>(Bop, c >> 3, n, c & 7, v);
+            sq = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+          }
+          if (owns_stat) {
+            // a warp's 32 consecutive chunks belong to one row (or straddle a row boundary): one smem atomic per warp
+            const unsigned am = __ballot_sync(0xffffffffu, act);
+            if (am != 0u) {
+              const int lo_l = __ffs(am) - 1, hi_l = 31 - __clz(am);
+              const int n_lo = __shfl_sync(0xffffffffu, n, lo_l), n_hi = __shfl_sync(0xffffffffu, n, hi_l);
+              if (n_lo == n_hi) {
+                const float s = warp_sum(sq);
+                if (lane == lo_l) atomicAdd(&sh.ss[n_lo], s);
+              } else if (act) {
+                atomicAdd(&sh.ss[n], sq);
+              }
+            }
+          }
+        }
       }
       b_publish();
+      if (owns_stat && ct < p.R) {
+        atomicAdd(stat_row + ct, sh.ss[ct]);
+        sh.ss[ct] = 0.f;
+      }
     };
     // epilogue of this CTA's tiles: TMEM -> red.add into out[n][col0 + row]
     auto epilogue = [&](const PcSlice& sl, float* out, int ldo, int M, int split_t, float* out2) {
@@ -582,25 +662,103 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         const int t = sl.t0 + i * sl.G;
         const uint32_t ab = tile_ctr & 1u, aph = (tile_ctr >> 1) & 1u;
         ++tile_ctr;
-        ptx::mbar_wait(ptx::smem_u32(acc_full + ab), aph);
-        ptx::tc_fence_after();
-        uint32_t acc[NB];
-        const uint32_t ta = tmem_base + ((uint32_t)(32 * quad) << 16) + ab * NB;
-        if (NB == 16) {
-          ptx::tmem_ld16(ta, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
-        } else {
-          ptx::tmem_ld16(ta, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
-          ptx::tmem_ld16(ta + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[NB - 16]));
-        }
-        ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(ptx::smem_u32(acc_empty + ab));
         float* o = (t < split_t) ? out : out2;
-        const int j = ((t < split_t) ? t : t - split_t) * 128 + 32 * quad + lane;
-        if (j < M) {
+        const int col0 = ((t < split_t) ? t : t - split_t) * TILE_ROWS;
+        if (WB) {
+          // accumulator = D[activation row (TMEM lane)][weight row (column)]: hi halves in lanes [0, RH), lo halves in
+          // lanes [RH, 2 RH) -- all inside lane quadrant 0, which only the compute warp with warp % 4 == 0 may read.
+          // That warp adds the CTA's split-K partial into out[n][col0 .. col0 + 255] with vectorised red.add.
+          if (quad != 0) continue;
+          ptx::mbar_wait(ptx::smem_u32(sh.acc_full + ab), aph);
+          ptx::tc_fence_after();
+          if (p.epi_mode == 2) {
+            // fragment loads: thread T owns activation rows T/4 and T/4 + 8 and two adjacent weight rows per 8 columns
+            const int qrow = lane >> 2, qcol = 2 * (lane & 3);
+            // NB = 16: lanes 0-7 = hi halves, 8-15 = lo halves of rows 0-7            -> one load, hi + lo inside the thread
+            // NB = 32: lanes 0-15 = hi halves of rows 0-15, lanes 16-31 = lo halves    -> two loads (lane offset 16)
+#pragma unroll 1
+            for (int c0 = 0; c0 < 256; c0 += 64) {
+              uint32_t va[32], vb[32];
+              tmem_ld_16x256b_x8(tmem_base + ab * 256 + c0, va);
+              if (NB == 32) tmem_ld_16x256b_x8(tmem_base + (16u << 16) + ab * 256 + c0, vb);
+              ptx::tmem_ld_wait();
+              if (c0 == 192) {                       // accumulator fully read: hand it back before the atomics
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(sh.acc_empty + ab));
+              }
 #pragma unroll
-          for (int n = 0; n < RH; ++n)
-            if (n < p.R) atomicAdd(o + (size_t)n * ldo + j, __uint_as_float(acc[n]) + __uint_as_float(acc[RH + n]));
+              for (int i = 0; i < 8; ++i) {
+                const int col = col0 + c0 + 8 * i + qcol;
+                if (NB == 16) {
+                  if (qrow < p.R) {
+                    float* orow = o + (size_t)qrow * ldo + col;
+                    if (col < M) atomicAdd(orow, __uint_as_float(va[4 * i]) + __uint_as_float(va[4 * i + 2]));
+                    if (col + 1 < M) atomicAdd(orow + 1, __uint_as_float(va[4 * i + 1]) + __uint_as_float(va[4 * i + 3]));
+                  }
+                } else {
+#pragma unroll
+                  for (int hrow = 0; hrow < 2; ++hrow) {
+                    const int n = qrow + 8 * hrow;
+                    if (n < p.R) {
+                      float* orow = o + (size_t)n * ldo + col;
+                      if (col < M) atomicAdd(orow, __uint_as_float(va[4 * i + 2 * hrow]) + __uint_as_float(vb[4 * i + 2 * hrow]));
+                      if (col + 1 < M) atomicAdd(orow + 1, __uint_as_float(va[4 * i + 2 * hrow + 1]) + __uint_as_float(vb[4 * i + 2 * hrow + 1]));
+                    }
+                  }
+                }
+              }
+            }
+            continue;
+          }
+          const bool vec = ((ldo & 3) == 0) && p.epi_mode == 0;
+#pragma unroll 1
+          for (int c0 = 0; c0 < 256; c0 += 64) {
+            uint32_t v[64];
+            tmem_ld64(tmem_base + ab * 256 + c0, v);
+            ptx::tmem_ld_wait();
+            if (c0 == 192) {                       // accumulator fully read: hand it back before the atomics
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(sh.acc_empty + ab));
+            }
+            float* orow = o + (size_t)lane * ldo + col0 + c0;
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+              float f[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float hi = __uint_as_float(v[j + e]);
+                f[e] = hi + __shfl_down_sync(0xffffffffu, hi, RH);   // lane n + RH: the lo-half product of row n
+              }
+              if (lane < p.R) {
+                const int col = col0 + c0 + j;
+                if (vec && col + 3 < M) {
+                  red_add_v4(orow + j, f[0], f[1], f[2], f[3]);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    if (col + e < M) atomicAdd(orow + j + e, f[e]);
+                }
+              }
+            }
+          }
+        } else {
+          ptx::mbar_wait(ptx::smem_u32(sh.acc_full + ab), aph);
+          ptx::tc_fence_after();
+          uint32_t acc[NB];
+          const uint32_t ta = tmem_base + ((uint32_t)(32 * quad) << 16) + ab * NB;
+          ptx::tmem_ld16(ta, *reinterpret_cast<uint32_t(*)[16]>(&acc[0]));
+          if (NB == 32) ptx::tmem_ld16(ta + 16, *reinterpret_cast<uint32_t(*)[16]>(&acc[NB - 16]));
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(ptx::smem_u32(sh.acc_empty + ab));
+          const int j = col0 + 32 * quad + lane;
+          if (j < M) {
+#pragma unroll
+            for (int n = 0; n < RH; ++n)
+              if (n < p.R) atomicAdd(o + (size_t)n * ldo + j, __uint_as_float(acc[n]) + __uint_as_float(acc[RH + n]));
+          }
         }
       }
     };
@@ -609,279 +767,536 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       const size_t b = (size_t)cta * per, e = min(n_floats / 4, b + per);
       for (size_t i = b + ct; i < e; i += 128) reinterpret_cast<float4*>(buf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     };
-
-    // ---- phase E: x = tok_emb + pos_emb + speaker (fast_model.py:152-157); CTA r builds row r
-    if (cta < p.R) {
-      const int u = p.st.slot_map[cta >> 1], c = cta & 1;
-      const __nv_bfloat16* te = p.tok_emb + (size_t)p.st.row_tok[2 * u + c] * p.D;
-      const __nv_bfloat16* pe = p.pos_emb + (size_t)p.st.pos[u] * p.D;
-      for (int d = ct; d < p.D; d += 128) {
-        float v = bf16_to_f32(te[d]) + bf16_to_f32(pe[d]);
-        if (c == 0) v += p.spk_proj[(size_t)u * p.D + d];
-        p.x[(size_t)cta * p.D + d] = v;
+    // Sampler bookkeeping of decode_n_tokens / generate (utils:160-172, 212-226) for the draw of step `s_step`: append,
+    // feed back, bump the position, latch end-of-audio / budget / context end.  EVERY CTA applies the same update to its
+    // private copy of the state (thread b handles batch entry b); the owner CTA 2b also writes it back.
+    auto finish_sample = [&](int s_step) {
+      if (ct < p.n_utts && !sh.st_done[ct]) {
+        const int b = ct, u = sh.c_slot[b];
+        const unsigned long long best = __ldcg(p.samp_best + (size_t)(s_step & 1) * (PC_RPAD / 2) + b);
+        const int tok = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
+        const int eoa = sh.c_samp[b].end_of_audio;
+        const int budget = sh.c_budget[b];
+        const int* forced = sh.c_forced[b];
+        const int n = sh.st_ngen[b];
+        const int fed = forced ? forced[n] : tok;
+        const int np = sh.st_pos[b] + 1;
+        const bool stop = fed == eoa || np >= p.st.block_size || n + 1 >= p.st.max_new || n + 1 >= budget;
+        if (cta == 2 * b) {
+          p.st.sampled_tokens[(size_t)u * p.st.max_new + n] = tok;
+          p.st.gen_tokens[(size_t)u * p.st.max_new + n] = fed;
+          p.st.row_tok[2 * u] = fed;
+          p.st.row_tok[2 * u + 1] = fed;
+          if (!stop) p.st.pos[u] = np;
+          p.st.n_gen[u] = n + 1;
+          if (stop) p.st.done[u] = 1;
+        }
+        sh.st_tok[2 * b] = fed;
+        sh.st_tok[2 * b + 1] = fed;
+        if (!stop) sh.st_pos[b] = np;
+        sh.st_ngen[b] = n + 1;
+        if (stop) sh.st_done[b] = 1;
       }
+      compute_sync();
+    };
+    const bool owner = cta < p.R && (cta & 1) == 0;   // CTA 2b writes batch entry b's state and x rows back to global memory
+    const int n_norm = 2 * p.n_layer + 1;
+    if (ct < p.n_utts) {                // decode state as the host / the previous launch left it
+      const int u = p.st.slot_map[ct];
+      sh.c_slot[ct] = u;
+      sh.c_samp[ct] = p.st.samp[u];
+      sh.c_noise[ct] = p.st.noise[u];
+      sh.c_forced[ct] = p.st.forced[u];
+      sh.c_budget[ct] = p.st.budget[u];
+      sh.c_nbase[ct] = p.st.noise_base[u];
+      sh.st_pos[ct] = p.st.pos[u];
+      sh.st_ngen[ct] = p.st.n_gen[u];
+      sh.st_done[ct] = p.st.done[u];
+      sh.st_tok[2 * ct] = p.st.row_tok[2 * u];
+      sh.st_tok[2 * ct + 1] = p.st.row_tok[2 * u + 1];
     }
-    stamp();
-    grid_arrive();
+    compute_sync();
 
-    for (int l = 0; l < p.n_layer; ++l) {
-      const size_t lo_ = (size_t)l * p.layer_stride;
-      // ---- QKV: B = RMSNorm(x) * attn_norm; out: qkv (zero on entry)
-      grid_wait();
+    for (int step = 0; step < p.n_steps; ++step) {
+      ev = 0;
       stamp();
-      stage_norm(s_qkv, p.attn_norm + lo_);
+      // ---- token start: bookkeeping of the previous draw; attention tile table; the owner CTA materialises the x rows
+      // (residual stream) in global memory -- they are first needed two grid barriers later (wo + residual), so nobody
+      // waits for them: the first QKV operand is staged straight from the embedding tables by every CTA.
+      if (step > 0 && p.fused) finish_sample(step - 1);
+      if (ct == 0) {
+        sh.n_att_tiles = build_att_table(p, sh.st_pos, sh.c_slot, cta, G, ppc, esz, sh.att_tab, sh.row_nz);
+        ptx::mbar_arrive(ptx::smem_u32(&sh.tab_ready));   // release: the producer may walk the table
+      }
+      if (owner) {
+        const int b = cta >> 1, u = sh.c_slot[b];
+        const __nv_bfloat16* pe = p.pos_emb + (size_t)min(sh.st_pos[b], p.S_max - 1) * p.D;
+        const __nv_bfloat16* te0 = p.tok_emb + (size_t)sh.st_tok[2 * b] * p.D;
+        const __nv_bfloat16* te1 = p.tok_emb + (size_t)sh.st_tok[2 * b + 1] * p.D;
+        for (int d = ct * 8; d < p.D; d += 128 * 8) {       // 8 elements per thread per trip, all loads issued together
+          const uint4 wp = *reinterpret_cast<const uint4*>(pe + d);
+          const uint4 w0 = *reinterpret_cast<const uint4*>(te0 + d);
+          const uint4 w1 = *reinterpret_cast<const uint4*>(te1 + d);
+          const float4 sa = *reinterpret_cast<const float4*>(p.spk_proj + (size_t)u * p.D + d);
+          const float4 sb = *reinterpret_cast<const float4*>(p.spk_proj + (size_t)u * p.D + d + 4);
+          const float pv[8] = {bf_lo(wp.x), bf_hi(wp.x), bf_lo(wp.y), bf_hi(wp.y), bf_lo(wp.z), bf_hi(wp.z), bf_lo(wp.w), bf_hi(wp.w)};
+          const float t0[8] = {bf_lo(w0.x), bf_hi(w0.x), bf_lo(w0.y), bf_hi(w0.y), bf_lo(w0.z), bf_hi(w0.z), bf_lo(w0.w), bf_hi(w0.w)};
+          const float t1[8] = {bf_lo(w1.x), bf_hi(w1.x), bf_lo(w1.y), bf_hi(w1.y), bf_lo(w1.z), bf_hi(w1.z), bf_lo(w1.w), bf_hi(w1.w)};
+          const float sv[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+          float r0[8], r1[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            r0[e] = (t0[e] + pv[e]) + sv[e];      // conditioned row: + speaker projection (fast_model.py:155-157)
+            r1[e] = t1[e] + pv[e];
+          }
+          float4* x0 = reinterpret_cast<float4*>(p.x + (size_t)cta * p.D + d);
+          float4* x1 = reinterpret_cast<float4*>(p.x + (size_t)(cta + 1) * p.D + d);
+          x0[0] = make_float4(r0[0], r0[1], r0[2], r0[3]); x0[1] = make_float4(r0[4], r0[5], r0[6], r0[7]);
+          x1[0] = make_float4(r1[0], r1[1], r1[2], r1[3]); x1[1] = make_float4(r1[4], r1[5], r1[6], r1[7]);
+        }
+      }
+      compute_sync();
       stamp();
-      epilogue(s_qkv, p.qkv, 3 * p.D, 3 * p.D, 1 << 30, nullptr);
-      stamp();
-      grid_arrive();
 
-      // ---- attention over [0, pos] + KV-cache append (fast_model.py:104-113, 220-224)
-      zero_slice(p.gu, (size_t)PC_RPAD * 2 * p.F);   // free since the previous layer's w2 phase; ordered by the next arrive
-      grid_wait();
-      stamp();
-      {
-        char* kbase = p.kv + (size_t)l * 2 * p.kv_half;
-        char* vbase = kbase + p.kv_half;
-        const int half = lane >> 4, sub = lane & 15;
-        const int hw = cw * 2 + half;               // half-warp id 0..7
-        const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
-        float q[8], o[8], m = -INFINITY, lsum = 0.f, kcur = 0.f, vcur = 0.f;
-        const int n_tiles = row_nz[PC_RPAD];
-        for (int ti = 0; ti < n_tiles; ++ti) {
-          const AttTile e = att_tab[ti];
-          const int npos = (int)(e.meta & 0xffu);
-          const bool has_cur = e.meta & 0x100u, unit_first = e.meta & 0x200u, unit_last = e.meta & 0x400u,
-                     owns_cur = e.meta & 0x800u;
-          const int r = e.where & 0xff, h = (e.where >> 8) & 0xff, z = (e.where >> 16) & 0xff, cr = e.where >> 24;
-          const int L = e.L;
-          if (unit_first) {
-            // ---- unit begin: one round trip for everything the unit needs from global memory
-            const float* qrow = p.qkv + (size_t)r * 3 * p.D + h * 128;
-            const float4 qa = __ldcg(reinterpret_cast<const float4*>(qrow + sub * 8));
-            const float4 qb = __ldcg(reinterpret_cast<const float4*>(qrow + sub * 8) + 1);
-            if (owns_cur) {
-              kcur = __ldcg(qrow + p.D + ct);
-              vcur = __ldcg(qrow + 2 * p.D + ct);
-            }
-            const float sc = 0.08838834764831845f;   // 1/sqrt(128)
-            q[0] = qa.x * sc; q[1] = qa.y * sc; q[2] = qa.z * sc; q[3] = qa.w * sc;
-            q[4] = qb.x * sc; q[5] = qb.y * sc; q[6] = qb.z * sc; q[7] = qb.w * sc;
-            m = -INFINITY; lsum = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = 0.f;
-          }
-          // ---- one KV tile (and, on the row's last tile, the current token)
-          if (has_cur) {
-            // append the new token's k, v to the cache, rounded as the cache stores them; share them via smem
-            const size_t ce = (((size_t)cr * p.H + h) * p.S_max + (L - 1)) * 128 + ct;
-            if (KV_FP32) {
-              reinterpret_cast<float*>(kbase)[ce] = kcur;
-              reinterpret_cast<float*>(vbase)[ce] = vcur;
-            } else {
-              const __nv_bfloat16 kb16 = __float2bfloat16_rn(kcur), vb16 = __float2bfloat16_rn(vcur);
-              reinterpret_cast<__nv_bfloat16*>(kbase)[ce] = kb16;
-              reinterpret_cast<__nv_bfloat16*>(vbase)[ce] = vb16;
-              kcur = __bfloat162float(kb16);
-              vcur = __bfloat162float(vb16);
-            }
-            sm_cur[ct] = kcur;
-            sm_cur[128 + ct] = vcur;
-          }
-          if (npos > 0) {
-            const uint32_t ks = kv_ctr % PC_NKV, ph = (kv_ctr / PC_NKV) & 1u;
-            ++kv_ctr;
-            ptx::mbar_wait(ptx::smem_u32(kv_full + ks), ph);
-            const uint8_t* kt = kvbuf + (size_t)ks * 2 * PC_STAGE_BYTES;
-            const uint8_t* vt = kt + PC_STAGE_BYTES;
-            // each half-warp owns positions hw, hw+8, ...; two positions per trip for ILP
-            for (int pb = hw; pb < npos; pb += 16) {
-              const int pA = pb, pB = pb + 8;
-              const bool vB = pB < npos;
-              float ka[8], kb2[8], sA = 0.f, sB = 0.f;
-              load8s<KV_FP32>(kt, pA, sub, ka);
-              if (vB) load8s<KV_FP32>(kt, pB, sub, kb2);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                sA = fmaf(q[i], ka[i], sA);
-                if (vB) sB = fmaf(q[i], kb2[i], sB);
+      for (int l = 0; l < p.n_layer; ++l) {
+        const size_t lo_ = (size_t)l * p.layer_stride;
+        float* stat_a = p.stat + (size_t)(2 * l) * PC_RPAD;
+        float* stat_f = stat_a + PC_RPAD;
+        // ---- QKV: operand = x * attn_norm; out: qkv (zero on entry)
+        if (l > 0) grid_wait();
+        stamp();
+        stage_norm(s_qkv, p.attn_norm + lo_, stat_a, cta < p.m_qkv.S, l == 0);
+        stamp();
+        epilogue(s_qkv, p.qkv, 3 * p.D, 3 * p.D, 1 << 30, nullptr);
+        stamp();
+        grid_arrive();
+
+        // ---- attention over [0, pos] + KV-cache append (fast_model.py:104-113, 220-224)
+        zero_slice(p.gu, (size_t)PC_RPAD * 2 * p.F);   // free since the previous layer's w2 phase; ordered by the next arrive
+        grid_wait();
+        stamp();
+        {
+          char* kbase = p.kv + (size_t)l * 2 * p.kv_half;
+          char* vbase = kbase + p.kv_half;
+          const int half = lane >> 4, sub = lane & 15;
+          const int hw = cw * 2 + half;               // half-warp id 0..7
+          const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
+          float q[8], o[8], m = -INFINITY, lsum = 0.f, kcur = 0.f, vcur = 0.f;
+          const int n_tiles = sh.n_att_tiles;
+          for (int ti = 0; ti < n_tiles; ++ti) {
+            const AttTile e = sh.att_tab[ti];
+            const int npos = (int)(e.meta & 0xffu);
+            const bool has_cur = e.meta & 0x100u, unit_first = e.meta & 0x200u, unit_last = e.meta & 0x400u,
+                       owns_cur = e.meta & 0x800u;
+            const int r = e.where & 0xff, h = (e.where >> 8) & 0xff, z = (e.where >> 16) & 0xff, cr = e.where >> 24;
+            const int L = e.L;
+            if (unit_first) {
+              // ---- unit begin: one round trip for everything the unit needs from global memory
+              const float* qrow = p.qkv + (size_t)r * 3 * p.D + h * 128;
+              const float4 qa = __ldcg(reinterpret_cast<const float4*>(qrow + sub * 8));
+              const float4 qb = __ldcg(reinterpret_cast<const float4*>(qrow + sub * 8) + 1);
+              const float ssr = __ldcg(stat_a + r);
+              if (owns_cur) {
+                kcur = __ldcg(qrow + p.D + ct);
+                vcur = __ldcg(qrow + 2 * p.D + ct);
               }
+              const float rsn = rsqrtf(ssr * inv_D + p.eps);      // RMSNorm scale of this row (fast_model.py:254-255)
+              const float sc = 0.08838834764831845f * rsn;        // 1/sqrt(128)
+              kcur *= rsn;
+              vcur *= rsn;
+              q[0] = qa.x * sc; q[1] = qa.y * sc; q[2] = qa.z * sc; q[3] = qa.w * sc;
+              q[4] = qb.x * sc; q[5] = qb.y * sc; q[6] = qb.z * sc; q[7] = qb.w * sc;
+              m = -INFINITY; lsum = 0.f;
 #pragma unroll
-              for (int off = 8; off > 0; off >>= 1) {   // reduce inside the 16-lane group only: trip counts differ per half-warp
-                sA += __shfl_xor_sync(hmask, sA, off);
-                sB += __shfl_xor_sync(hmask, sB, off);
+              for (int i = 0; i < 8; ++i) o[i] = 0.f;
+            }
+            // ---- one KV tile (and, on the row's last tile, the current token)
+            if (has_cur) {
+              // append the new token's k, v to the cache, rounded as the cache stores them; share them via smem
+              const size_t ce = (((size_t)cr * p.H + h) * p.S_max + (L - 1)) * 128 + ct;
+              if (KV_FP32) {
+                reinterpret_cast<float*>(kbase)[ce] = kcur;
+                reinterpret_cast<float*>(vbase)[ce] = vcur;
+              } else {
+                const __nv_bfloat16 kb16 = __float2bfloat16_rn(kcur), vb16 = __float2bfloat16_rn(vcur);
+                reinterpret_cast<__nv_bfloat16*>(kbase)[ce] = kb16;
+                reinterpret_cast<__nv_bfloat16*>(vbase)[ce] = vb16;
+                kcur = __bfloat162float(kb16);
+                vcur = __bfloat162float(vb16);
               }
-              load8s<KV_FP32>(vt, pA, sub, ka);
-              if (vB) load8s<KV_FP32>(vt, pB, sub, kb2);
-              const float mn = fmaxf(m, vB ? fmaxf(sA, sB) : sA);
-              const float corr = __expf(m - mn), wA = __expf(sA - mn), wB = vB ? __expf(sB - mn) : 0.f;
-              lsum = lsum * corr + wA + wB;
+              // the next token's KV tiles are fetched with cp.async.bulk (async proxy) inside this same launch
+              asm volatile("fence.proxy.async.global;" ::: "memory");
+              sh.cur[ct] = kcur;
+              sh.cur[128 + ct] = vcur;
+            }
+            if (npos > 0) {
+              const uint32_t ks = kv_ctr % PC_NKV, ph = (kv_ctr / PC_NKV) & 1u;
+              ++kv_ctr;
+              ptx::mbar_wait(ptx::smem_u32(sh.kv_full + ks), ph);
+              const uint8_t* kt = kvbuf + (size_t)ks * 2 * PC_KV_TILE_BYTES;
+              const uint8_t* vt = kt + PC_KV_TILE_BYTES;
+              // each half-warp owns positions hw, hw+8, ...; two positions per trip for ILP
+              for (int pb = hw; pb < npos; pb += 16) {
+                const int pA = pb, pB = pb + 8;
+                const bool vB = pB < npos;
+                float ka[8], kb2[8], sA = 0.f, sB = 0.f;
+                load8s<KV_FP32>(kt, pA, sub, ka);
+                if (vB) load8s<KV_FP32>(kt, pB, sub, kb2);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + wA * ka[i] + (vB ? wB * kb2[i] : 0.f);
+                for (int i = 0; i < 8; ++i) {
+                  sA = fmaf(q[i], ka[i], sA);
+                  if (vB) sB = fmaf(q[i], kb2[i], sB);
+                }
+#pragma unroll
+                for (int off = 8; off > 0; off >>= 1) {   // reduce inside the 16-lane group only: trip counts differ per half-warp
+                  sA += __shfl_xor_sync(hmask, sA, off);
+                  sB += __shfl_xor_sync(hmask, sB, off);
+                }
+                load8s<KV_FP32>(vt, pA, sub, ka);
+                if (vB) load8s<KV_FP32>(vt, pB, sub, kb2);
+                const float mn = fmaxf(m, vB ? fmaxf(sA, sB) : sA);
+                const float corr = __expf(m - mn), wA = __expf(sA - mn), wB = vB ? __expf(sB - mn) : 0.f;
+                lsum = lsum * corr + wA + wB;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + wA * ka[i] + (vB ? wB * kb2[i] : 0.f);
+                m = mn;
+              }
+            }
+            if (npos > 0 || has_cur) compute_sync();   // KV tile fully consumed; sh.cur visible
+            if (npos > 0 && ct == 0) ptx::mbar_arrive(ptx::smem_u32(sh.kv_empty + ((kv_ctr - 1) % PC_NKV)));
+            if (has_cur && hw == 0) {
+              float sdot = 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) sdot = fmaf(q[i], sh.cur[sub * 8 + i], sdot);
+#pragma unroll
+              for (int off = 8; off > 0; off >>= 1) sdot += __shfl_xor_sync(0x0000ffffu, sdot, off);
+              const float mn = fmaxf(m, sdot), corr = __expf(m - mn), pw = __expf(sdot - mn);
+              lsum = lsum * corr + pw;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + pw * sh.cur[128 + sub * 8 + i];
               m = mn;
             }
+            if (unit_last) {
+              // ---- unit end: merge the 8 half-warp states -> one partial (m, l, o[128]) for split z
+              if (sub == 0) { sh.m[hw] = m; sh.l[hw] = lsum; }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) sh.o[hw * 128 + sub * 8 + i] = o[i];
+              compute_sync();
+              {
+                float M = -INFINITY;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) M = fmaxf(M, sh.m[i]);
+                float Ls = 0.f, O = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (sh.m[i] > -INFINITY) {
+                    const float w = __expf(sh.m[i] - M);
+                    Ls += sh.l[i] * w;
+                    O += sh.o[i * 128 + ct] * w;
+                  }
+                const size_t pidx = ((size_t)r * p.H + h) * PC_MAX_CHUNKS + z;
+                p.part_o[pidx * 128 + ct] = O;
+                if (ct == 0) { p.part_ml[pidx * 2] = M; p.part_ml[pidx * 2 + 1] = Ls; }
+              }
+              compute_sync();   // sh.o / sh.m / sh.cur are reused by the next unit
+            }
           }
-          if (npos > 0 || has_cur) compute_sync();   // KV tile fully consumed; sm_cur visible
-          if (npos > 0 && ct == 0) ptx::mbar_arrive(ptx::smem_u32(kv_empty + ((kv_ctr - 1) % PC_NKV)));
-          if (has_cur && hw == 0) {
-            float sdot = 0.f;
+        }
+        stamp();
+        grid_arrive();
+
+        // ---- wo + residual: operand = merged attention output (columns = this CTA's K range of heads)
+        grid_wait();
+        stamp();
+        if (s_o.nt > 0) {
+          const int nchunk = (s_o.kb1 - s_o.kb0) * 8;
+          for (int i = ct; i < p.R * nchunk; i += 128) {
+            const int n = i / nchunk, c = i - n * nchunk;
+            const int k = s_o.kb0 * 64 + c * 8;
+            const int h = k >> 7, d0 = k & 127;
+            const int nch = sh.row_nz[n];
+            const size_t pb = ((size_t)n * p.H + h) * PC_MAX_CHUNKS;
+            float M = -INFINITY;
+            float den = 0.f, v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sdot = fmaf(q[i], sm_cur[sub * 8 + i], sdot);
+            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+            if (nch <= 4) {
+              // one round trip: (m, l) and o of every split are requested together
+              float2 ml[4];
+              float4 oa[4], ob[4];
 #pragma unroll
-            for (int off = 8; off > 0; off >>= 1) sdot += __shfl_xor_sync(0x0000ffffu, sdot, off);
-            const float mn = fmaxf(m, sdot), corr = __expf(m - mn), pw = __expf(sdot - mn);
-            lsum = lsum * corr + pw;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + pw * sm_cur[128 + sub * 8 + i];
-            m = mn;
-          }
-          if (unit_last) {
-            // ---- unit end: merge the 8 half-warp states -> one partial (m, l, o[128]) for split z
-            if (sub == 0) { sm_m[hw] = m; sm_l[hw] = lsum; }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) sm_o[hw * 128 + sub * 8 + i] = o[i];
-            compute_sync();
-            {
-              float M = -INFINITY;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) M = fmaxf(M, sm_m[i]);
-              float Ls = 0.f, O = 0.f;
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (sm_m[i] > -INFINITY) {
-                  const float w = __expf(sm_m[i] - M);
-                  Ls += sm_l[i] * w;
-                  O += sm_o[i * 128 + ct] * w;
+              for (int z = 0; z < 4; ++z)
+                if (z < nch) {
+                  ml[z] = __ldcg(reinterpret_cast<const float2*>(p.part_ml + (pb + z) * 2));
+                  const float4* po = reinterpret_cast<const float4*>(p.part_o + (pb + z) * 128 + d0);
+                  oa[z] = __ldcg(po);
+                  ob[z] = __ldcg(po + 1);
                 }
-              const size_t pidx = ((size_t)r * p.H + h) * PC_MAX_CHUNKS + z;
-              p.part_o[pidx * 128 + ct] = O;
-              if (ct == 0) { p.part_ml[pidx * 2] = M; p.part_ml[pidx * 2 + 1] = Ls; }
-            }
-            compute_sync();   // sm_o / sm_m / sm_cur are reused by the next unit
-          }
-        }
-      }
-      stamp();
-      grid_arrive();
-
-      // ---- wo + residual: B = merged attention output (columns = this CTA's K range of heads)
-      grid_wait();
-      stamp();
-      if (s_o.nt > 0) {
-        const int nchunk = (s_o.kb1 - s_o.kb0) * 8;
-        for (int i = ct; i < p.R * nchunk; i += 128) {
-          const int n = i / nchunk, c = i - n * nchunk;
-          const int k = s_o.kb0 * 64 + c * 8;
-          const int h = k >> 7, d0 = k & 127;
-          const int nch = row_nz[n];
-          const size_t pb = ((size_t)n * p.H + h) * PC_MAX_CHUNKS;
-          float M = -INFINITY;
-          float den = 0.f, v[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.f;
-          if (nch <= 4) {
-            // one round trip: (m, l) and o of every split are requested together
-            float2 ml[4];
-            float4 oa[4], ob[4];
+              for (int z = 0; z < 4; ++z)
+                if (z < nch) M = fmaxf(M, ml[z].x);
 #pragma unroll
-            for (int z = 0; z < 4; ++z)
-              if (z < nch) {
-                ml[z] = __ldcg(reinterpret_cast<const float2*>(p.part_ml + (pb + z) * 2));
+              for (int z = 0; z < 4; ++z)
+                if (z < nch) {
+                  const float w = __expf(ml[z].x - M);
+                  den += ml[z].y * w;
+                  v[0] += oa[z].x * w; v[1] += oa[z].y * w; v[2] += oa[z].z * w; v[3] += oa[z].w * w;
+                  v[4] += ob[z].x * w; v[5] += ob[z].y * w; v[6] += ob[z].z * w; v[7] += ob[z].w * w;
+                }
+            } else {
+              for (int z = 0; z < nch; ++z) M = fmaxf(M, __ldcg(p.part_ml + (pb + z) * 2));
+              for (int z = 0; z < nch; ++z) {
+                const float w = __expf(__ldcg(p.part_ml + (pb + z) * 2) - M);
+                den += __ldcg(p.part_ml + (pb + z) * 2 + 1) * w;
                 const float4* po = reinterpret_cast<const float4*>(p.part_o + (pb + z) * 128 + d0);
-                oa[z] = __ldcg(po);
-                ob[z] = __ldcg(po + 1);
+                const float4 a = __ldcg(po), b = __ldcg(po + 1);
+                v[0] += a.x * w; v[1] += a.y * w; v[2] += a.z * w; v[3] += a.w * w;
+                v[4] += b.x * w; v[5] += b.y * w; v[6] += b.z * w; v[7] += b.w * w;
               }
+            }
+            const float inv = 1.f / den;
 #pragma unroll
-            for (int z = 0; z < 4; ++z)
-              if (z < nch) M = fmaxf(M, ml[z].x);
+            for (int e = 0; e < 8; ++e) v[e] *= inv;
+            b_store8<NB>(Bop, c >> 3, n, c & 7, v);
+          }
+          b_publish();
+        }
+        stamp();
+        epilogue(s_o, p.x, p.D, p.D, 1 << 30, nullptr);
+        stamp();
+        grid_arrive();
+        zero_slice(p.qkv, (size_t)PC_RPAD * 3 * p.D);  // q, k, v were consumed by the attention phase; ordered by the next arrive
+
+        // ---- w1 | w3: operand = x * ffn_norm; out: g | u (zero on entry)
+        grid_wait();
+        stamp();
+        stage_norm(s_w13, p.ffn_norm + lo_, stat_f, cta < p.m_w13.S, false);
+        stamp();
+        epilogue(s_w13, p.gu, 2 * p.F, p.F, T1, p.gu + p.F);
+        stamp();
+        grid_arrive();
+
+        // ---- w2 + residual: operand = silu(rs g) * (rs u) (fast_model.py:237, with the RMSNorm scale of the ffn input)
+        grid_wait();
+        stamp();
+        if (s_w2.nt > 0) {
+          const int nchunk = (s_w2.kb1 - s_w2.kb0) * 8;
+          const int total = p.R * nchunk;
+          for (int i0 = ct; i0 < total; i0 += 2 * 128) {
+            float4 g0[2], g1[2], u0[2], u1[2];
+            float ssn[2];
 #pragma unroll
-            for (int z = 0; z < 4; ++z)
-              if (z < nch) {
-                const float w = __expf(ml[z].x - M);
-                den += ml[z].y * w;
-                v[0] += oa[z].x * w; v[1] += oa[z].y * w; v[2] += oa[z].z * w; v[3] += oa[z].w * w;
-                v[4] += ob[z].x * w; v[5] += ob[z].y * w; v[6] += ob[z].z * w; v[7] += ob[z].w * w;
+            for (int j = 0; j < 2; ++j) {
+              const int i = i0 + j * 128;
+              if (i < total) {
+                const int n = i / nchunk, c = i - n * nchunk;
+                const int k = s_w2.kb0 * 64 + c * 8;
+                const float4* gp = reinterpret_cast<const float4*>(p.gu + (size_t)n * 2 * p.F + k);
+                const float4* up = reinterpret_cast<const float4*>(p.gu + (size_t)n * 2 * p.F + p.F + k);
+                g0[j] = __ldcg(gp); g1[j] = __ldcg(gp + 1); u0[j] = __ldcg(up); u1[j] = __ldcg(up + 1);
+                ssn[j] = __ldcg(stat_f + n);
               }
-          } else {
-            for (int z = 0; z < nch; ++z) M = fmaxf(M, __ldcg(p.part_ml + (pb + z) * 2));
-            for (int z = 0; z < nch; ++z) {
-              const float w = __expf(__ldcg(p.part_ml + (pb + z) * 2) - M);
-              den += __ldcg(p.part_ml + (pb + z) * 2 + 1) * w;
-              const float4* po = reinterpret_cast<const float4*>(p.part_o + (pb + z) * 128 + d0);
-              const float4 a = __ldcg(po), b = __ldcg(po + 1);
-              v[0] += a.x * w; v[1] += a.y * w; v[2] += a.z * w; v[3] += a.w * w;
-              v[4] += b.x * w; v[5] += b.y * w; v[6] += b.z * w; v[7] += b.w * w;
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int i = i0 + j * 128;
+              if (i < total) {
+                const int n = i / nchunk, c = i - n * nchunk;
+                const float rs = rsqrtf(ssn[j] * inv_D + p.eps);
+                const float g[8] = {g0[j].x, g0[j].y, g0[j].z, g0[j].w, g1[j].x, g1[j].y, g1[j].z, g1[j].w};
+                const float uu[8] = {u0[j].x, u0[j].y, u0[j].z, u0[j].w, u1[j].x, u1[j].y, u1[j].z, u1[j].w};
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float ge = g[e] * rs;
+                  v[e] = __fdividef(ge, 1.f + __expf(-ge)) * (uu[e] * rs);   // SiLU, 2-ulp division
+                }
+                b_store8<NB>(Bop, c >> 3, n, c & 7, v);
+              }
             }
           }
-          const float inv = 1.f / den;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] *= inv;
-          b_store8<NB>(Bop, c >> 3, n, c & 7, v);
+          b_publish();
         }
-        b_publish();
+        stamp();
+        epilogue(s_w2, p.x, p.D, p.D, 1 << 30, nullptr);
+        stamp();
+        grid_arrive();
+      }
+      // ---- head: logits += (x * out_norm) . W_out^T   (rows n = batch order; scaled by the final RMSNorm below)
+      float* stat_h = p.stat + (size_t)(2 * p.n_layer) * PC_RPAD;
+      grid_wait();
+      zero_slice(p.gu, (size_t)PC_RPAD * 2 * p.F);
+      stamp();
+      stage_norm(s_head, p.out_norm, stat_h, cta < p.m_head.S, false);
+      stamp();
+      epilogue(s_head, p.logits, p.V, p.V, 1 << 30, nullptr);
+      stamp();
+      grid_arrive();
+      grid_wait();                        // logits (un-normalised) and the final statistic are complete
+      stamp();
+      const int V = p.V;
+      if (!p.fused) {
+        // parity / legacy-sampler mode: apply the final RMSNorm scale in place, this CTA's share of the R rows
+        const int tot = p.R * V, per = (tot + G - 1) / G;
+        for (int i = cta * per + ct; i < min(tot, (cta + 1) * per); i += 128) {
+          const int n = i / V;
+          p.logits[i] *= rsqrtf(__ldcg(stat_h + n) * inv_D + p.eps);
+        }
+      } else {
+        // ================= grid-distributed sampler == sample() (fast_inference_utils.py:61-120), top_k = None ==========
+        // CFG mix, temperature, softmax, top-p over the ASCENDING order (drop cum <= 1-p, never the last), softmax of
+        // the kept entries, arg-max of probs / Exp(1).  No sort: entry i's cumulative mass is the sum of e_j over all j
+        // ordered before-or-at i; every CTA evaluates it for its own ~V/grid entries against the whole vocabulary.
+        float* s_key = reinterpret_cast<float*>(kvbuf);   // [V] (the KV tile slots are idle between tokens)
+        float* s_e = s_key + SAMP_PAD;
+        const int per = (V + G - 1) / G;
+        const int i0 = cta * per, n_own = max(0, min(V, i0 + per) - i0);
+        for (int b = 0; b < p.n_utts; ++b) {
+          if (sh.st_done[b]) continue;
+          const SamplingDev sp = sh.c_samp[b];
+          const float* lc = p.logits + (size_t)(2 * b) * V;
+          const float* lu = lc + V;
+          const float rs_c = rsqrtf(__ldcg(stat_h + 2 * b) * inv_D + p.eps), rs_u = rsqrtf(__ldcg(stat_h + 2 * b + 1) * inv_D + p.eps);
+          // CFG mix and temperature, with torch's rounding order (utils:116, :92)
+          const float g = sp.guidance, omg = __fsub_rn(1.0f, sp.guidance);
+          const float tdiv = fmaxf(sp.temperature, 1e-5f);
+          float mx = -INFINITY;
+          for (int v0 = ct; v0 < V; v0 += 24 * 128) {       // up to 48 loads in flight per thread: one L2 round trip for V <= 3072
+            float la[24], lb[24];
+#pragma unroll
+            for (int i = 0; i < 24; ++i) {
+              const int v = v0 + i * 128;
+              if (v < V) { la[i] = __ldcg(lc + v); lb[i] = __ldcg(lu + v); }
+            }
+#pragma unroll
+            for (int i = 0; i < 24; ++i) {
+              const int v = v0 + i * 128;
+              if (v < V) {
+                const float k = __fdiv_rn(__fadd_rn(__fmul_rn(g, la[i] * rs_c), __fmul_rn(omg, lb[i] * rs_u)), tdiv);
+                s_key[v] = k;
+                mx = fmaxf(mx, k);
+              }
+            }
+          }
+          if (b == 0) stamp();
+          mx = block_max(mx);
+          float zs = 0.f;
+          for (int v = ct; v < V; v += 128) {
+            const float e = expf(s_key[v] - mx);
+            s_e[v] = e;
+            zs += e;
+          }
+          const float Z = block_sum(zs);      // (block_sum's barriers also publish s_key / s_e)
+          if (b == 0) stamp();
+          // own entries: warp cw takes entries cw, cw + 4, ...; lanes stride over the vocabulary
+          {
+            constexpr int TPW = PC_SAMP_OWN / 4;
+            float ki[TPW], acc[TPW];
+            int after[TPW], ii[TPW];
+#pragma unroll
+            for (int t = 0; t < TPW; ++t) {
+              ii[t] = i0 + cw + 4 * t;
+              ki[t] = (cw + 4 * t < n_own) ? s_key[ii[t]] : INFINITY;
+              acc[t] = 0.f;
+              after[t] = 0;
+            }
+            const int nt_w = (n_own > cw) ? (n_own - cw + 3) / 4 : 0;
+            if (nt_w > 0) {
+#pragma unroll 4
+              for (int j = lane; j < V; j += 32) {
+                const float kj = s_key[j], ej = s_e[j];
+#pragma unroll
+                for (int t = 0; t < TPW; ++t) {
+                  // ascending order, ties by index (stable); bitwise predicate logic: no divergent short-circuit branches
+                  const bool before = (kj < ki[t]) | ((kj == ki[t]) & (j <= ii[t]));
+                  acc[t] += before ? ej : 0.f;
+                  after[t] += before ? 0 : 1;
+                }
+              }
+            }
+            const bool use_p = sp.top_p > 0.f;
+            const float thr = __fsub_rn(1.0f, sp.top_p);
+#pragma unroll
+            for (int t = 0; t < TPW; ++t) {
+              const float cum = warp_sum(acc[t]);
+              int na = after[t];
+#pragma unroll
+              for (int o2 = 16; o2 > 0; o2 >>= 1) na += __shfl_xor_sync(0xffffffffu, na, o2);
+              if (lane == 0 && cw + 4 * t < n_own) {
+                const bool drop = use_p && (cum / Z <= thr) && (na != 0);   // never the last (largest) entry (utils:75-77)
+                sh.own_ke[b][cw + 4 * t] = drop ? 0.f : s_e[ii[t]];
+              }
+            }
+          }
+          if (b == 0) stamp();
+          compute_sync();
+          if (ct == 0) {
+            float ps = 0.f;
+            for (int t = 0; t < n_own; ++t) ps += sh.own_ke[b][t];
+            p.samp_part[(size_t)b * G + cta] = ps;
+          }
+          compute_sync();                     // s_key / s_e are rewritten for the next utterance
+        }
+        stamp();
+        grid_arrive();
+        grid_wait();                          // every CTA's kept mass is visible; nobody reads the logits any more
+        stamp();
+        zero_slice(p.logits, (size_t)p.R * V);   // hand the accumulation rows back zeroed (ordered by the next arrive)
+        if (cta == 0) {
+          // every RMSNorm statistic of this token has been consumed (the last one by the sampler above); the arg-max
+          // slots of the PREVIOUS draw have been read by every CTA's bookkeeping (they all passed this token's barriers)
+          for (int i = ct; i < n_norm * PC_RPAD; i += 128) p.stat[i] = 0.f;
+          if (ct < PC_RPAD / 2) p.samp_best[(size_t)((step & 1) ^ 1) * (PC_RPAD / 2) + ct] = 0ull;
+        }
+        for (int b = 0; b < p.n_utts; ++b) {
+          const int u = sh.c_slot[b];
+          if (sh.st_done[b]) continue;
+          float part = 0.f;
+          for (int c = ct; c < G; c += 128) part += __ldcg(p.samp_part + (size_t)b * G + c);
+          const float kept_total = block_sum(part);   // identical in every CTA (same order)
+          unsigned long long best = 0ull;
+          if (ct < n_own) {
+            const int v = i0 + ct;
+            const SamplingDev sp = sh.c_samp[b];
+            const int n_gen_u = sh.st_ngen[b];
+            const unsigned long long stp = (unsigned long long)n_gen_u;
+            const float* nz = sh.c_noise[b];
+            const float pr = sh.own_ke[b][ct] / kept_total;
+            float qv;
+            if (nz) {
+              qv = __ldcg(nz + (size_t)(n_gen_u - sh.c_nbase[b]) * V + v);
+            } else {
+              const uint4 rnd = philox4x32_10(make_uint4((unsigned)v, (unsigned)stp, (unsigned)(stp >> 32), (unsigned)u),
+                                              make_uint2((unsigned)sp.seed, (unsigned)(sp.seed >> 32)));
+              const float uni = ((float)(rnd.x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+              qv = -logf(uni);
+            }
+            const float score = __fdiv_rn(pr, qv);
+            // order-preserving key for non-negative floats; ties resolve to the lowest index like torch.argmax
+            best = ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(0xffffffffu - (unsigned)v);
+          }
+#pragma unroll
+          for (int o2 = 16; o2 > 0; o2 >>= 1) {
+            const unsigned long long n2 = __shfl_xor_sync(0xffffffffu, best, o2);
+            best = n2 > best ? n2 : best;
+          }
+          if (lane == 0) sh.best[cw] = best;
+          compute_sync();
+          if (ct == 0 && n_own > 0) {
+            unsigned long long bb = sh.best[0];
+            for (int w2 = 1; w2 < 4; ++w2) bb = sh.best[w2] > bb ? sh.best[w2] : bb;
+            atomicMax(p.samp_best + (size_t)(step & 1) * (PC_RPAD / 2) + b, bb);
+          }
+          compute_sync();
+        }
+        stamp();
+        grid_arrive();
+        grid_wait();                          // the arg-max of every utterance is complete
       }
       stamp();
-      epilogue(s_o, p.x, p.D, p.D, 1 << 30, nullptr);
-      stamp();
-      grid_arrive();
-      zero_slice(p.qkv, (size_t)PC_RPAD * 3 * p.D);  // q, k, v were consumed by the attention phase; ordered by the next arrive
-
-      // ---- w1 | w3: B = RMSNorm(x) * ffn_norm; out: g | u (zero on entry)
-      grid_wait();
-      stamp();
-      stage_norm(s_w13, p.ffn_norm + lo_);
-      stamp();
-      epilogue(s_w13, p.gu, 2 * p.F, p.F, T1, p.gu + p.F);
-      stamp();
-      grid_arrive();
-
-      // ---- w2 + residual: B = silu(g) * u (fast_model.py:237)
-      grid_wait();
-      stamp();
-      if (s_w2.nt > 0) {
-        const int nchunk = (s_w2.kb1 - s_w2.kb0) * 8;
-        const int total = p.R * nchunk;
-        for (int i0 = ct; i0 < total; i0 += 2 * 128) {
-          float4 g0[2], g1[2], u0[2], u1[2];
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int i = i0 + j * 128;
-            if (i < total) {
-              const int n = i / nchunk, c = i - n * nchunk;
-              const int k = s_w2.kb0 * 64 + c * 8;
-              const float4* gp = reinterpret_cast<const float4*>(p.gu + (size_t)n * 2 * p.F + k);
-              const float4* up = reinterpret_cast<const float4*>(p.gu + (size_t)n * 2 * p.F + p.F + k);
-              g0[j] = __ldcg(gp); g1[j] = __ldcg(gp + 1); u0[j] = __ldcg(up); u1[j] = __ldcg(up + 1);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int i = i0 + j * 128;
-            if (i < total) {
-              const int n = i / nchunk, c = i - n * nchunk;
-              const float g[8] = {g0[j].x, g0[j].y, g0[j].z, g0[j].w, g1[j].x, g1[j].y, g1[j].z, g1[j].w};
-              const float uu[8] = {u0[j].x, u0[j].y, u0[j].z, u0[j].w, u1[j].x, u1[j].y, u1[j].z, u1[j].w};
-              float v[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = (g[e] / (1.f + __expf(-g[e]))) * uu[e];
-              b_store8<NB>(Bop, c >> 3, n, c & 7, v);
-            }
-          }
-        }
-        b_publish();
-      }
-      stamp();
-      epilogue(s_w2, p.x, p.D, p.D, 1 << 30, nullptr);
-      stamp();
-      grid_arrive();
     }
-    // ---- head: logits += RMSNorm(x) * out_norm . W_out^T   (rows n = batch order = sampler rows 2u, 2u+1)
-    grid_wait();
-    zero_slice(p.gu, (size_t)PC_RPAD * 2 * p.F);
-    stamp();
-    stage_norm(s_head, p.out_norm);
-    stamp();
-    epilogue(s_head, p.logits, p.V, p.V, 1 << 30, nullptr);
-    stamp();
+    // bookkeeping of the last draw (no further position to embed)
+    if (p.fused) finish_sample(p.n_steps - 1);
     ptx::tc_fence_before();
   }
   __syncthreads();

@@ -56,7 +56,7 @@ struct WsLayout {
   // path B (tensor-core rows path): activations for up to RB_MAX rows
   size_t b_x, b_qkv, b_att, b_ffn, b_logits, b_last, b_B, b_rows, b_scratch, b_tickets, b_part_o, b_part_ml, b_att_tickets;
   // path C (persistent decode kernel)
-  size_t c_x, c_qkv, c_gu, c_part_o, c_part_ml, c_bar, c_trace;
+  size_t c_x, c_qkv, c_gu, c_part_o, c_part_ml, c_bar, c_trace, c_stat, c_samp_part, c_samp_best;
   size_t total;
 };
 
@@ -123,6 +123,9 @@ static WsLayout make_layout(const mvb_s1_config& c) {
   L.c_part_ml = take((size_t)PC_RPAD * H * PC_MAX_CHUNKS * 2 * 4);
   L.c_bar = take(256);
   L.c_trace = take((size_t)160 * PC_TRACE_EVENTS * 8);
+  L.c_stat = take((size_t)(2 * c.n_layer + 1) * PC_RPAD * 4);
+  L.c_samp_part = take((size_t)(PC_RPAD / 2) * 256 * 4);
+  L.c_samp_best = take((size_t)2 * (PC_RPAD / 2) * 8);
   L.total = o;
   return L;
 }
@@ -154,11 +157,14 @@ struct mvb_s1 {
   bool path_c = true;
   bool pc_ok = false;
   bool trace = false;
-  bool a_sw32 = false;
-  int pf_ahead = 8;
-  int pc_ts = 0, pc_nprod = 1;                        // experiment switches, read once at create (MVB_PC_TS, MVB_PC_NPROD)
-  CUtensorMap tm3[6];                                 // 3-D (k, row, layer) maps: wqkv, wo, w1, w3, w2, head
-  PcMat pm[5];
+  // persistent-kernel switches, read once at create (MVB_PC_WB, MVB_PC_FUSED, MVB_PF_MODE, MVB_PF_AHEAD)
+  bool wb = true;                                     // streamed weights as the N = 256 UMMA B operand
+  bool fused = true;                                  // sample inside the persistent kernel (multi-token launches)
+  int pf_mode = 1, pf_ahead = 8, epi_mode = 2;
+  CUtensorMap tm3[2][6];                              // [WB] 3-D (k, row, layer) maps: wqkv, wo, w1, w3, w2, head
+  PcMat pm[2][5];
+  bool pc_ok2[2] = {false, false};
+  std::vector<int> h_topk;                            // top_k of every utterance slot as installed by mvb_s1_begin
   size_t layer_stride_elems = 0;
 
   template <typename T>
@@ -174,24 +180,24 @@ struct mvb_s1 {
 
 // 3-D tensor map over one matrix kind of every layer: dims {K, M, n_layer}, tile {64, 128, 1}, 128B swizzle.
 static bool make_tmap_bf16_3d(CUtensorMap* tm, const void* ptr, uint64_t K, uint64_t M, uint64_t L, uint64_t layer_stride_bytes,
-                              bool sw32 = false) {
+                              uint32_t tile_rows) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   cuuint64_t dims[3] = {K, M, L};
   cuuint64_t strides[2] = {K * 2, layer_stride_bytes};
-  cuuint32_t box[3] = {sw32 ? 16u : 64u, 128, 1};
+  cuuint32_t box[3] = {64u, tile_rows, 1};              // rows past M read as zero
   cuuint32_t estr[3] = {1, 1, 1};
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, sw32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // Static decomposition of one matrix over `ctas` CTAs: the K split that minimises the busiest CTA's k-blocks.
-static PcMat plan_pc(int M, int K, int ctas) {
+static PcMat plan_pc(int M, int K, int ctas, int tile_rows) {
   PcMat best{};
   long best_cost = -1;
-  const int T = (M + 127) / 128, KB = K / 64;
-  for (int S = 1; S <= KB && S <= 16 && S <= ctas; ++S) {
+  const int T = (M + tile_rows - 1) / tile_rows, KB = K / 64;
+  for (int S = 1; S <= KB && S <= 32 && S <= ctas; ++S) {
     const int Gp = ctas / S;
     const int tiles_per = (T + Gp - 1) / Gp;
     const int kb_per = (KB + S - 1) / S;
@@ -298,8 +304,11 @@ extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size
   if (const char* e = getenv("MVB_PATHC")) h->path_c = atoi(e) != 0;
   if (const char* e = getenv("MVB_PC_TRACE")) h->trace = atoi(e) != 0;
   if (const char* e = getenv("MVB_PF_AHEAD")) h->pf_ahead = atoi(e);
-  if (const char* e = getenv("MVB_PC_TS")) h->pc_ts = atoi(e);
-  if (const char* e = getenv("MVB_PC_NPROD")) h->pc_nprod = (atoi(e) == 2) ? 2 : 1;
+  if (const char* e = getenv("MVB_PF_MODE")) h->pf_mode = atoi(e);
+  if (const char* e = getenv("MVB_PC_EPI")) h->epi_mode = atoi(e);
+  if (const char* e = getenv("MVB_PC_WB")) h->wb = atoi(e) != 0;
+  if (const char* e = getenv("MVB_PC_FUSED")) h->fused = atoi(e) != 0;
+  h->h_topk.assign(cfg->max_utts, 0);
   {
     // persistent decode kernel: needs a uniform layer stride (true for arenas packed in checkpoint order)
     const int D = cfg->dim, F = cfg->intermediate, V = cfg->vocab;
@@ -312,27 +321,36 @@ extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size
     ok = ok && (stride % 16 == 0);
     h->layer_stride_elems = stride / 2;
     const uint64_t NL = cfg->n_layer;
-    ok = ok && make_tmap_bf16_3d(&h->tm3[0], h->lw(0, 1), D, 3 * D, NL, stride, h->a_sw32);
-    ok = ok && make_tmap_bf16_3d(&h->tm3[1], h->lw(0, 2), D, D, NL, stride, h->a_sw32);
-    ok = ok && make_tmap_bf16_3d(&h->tm3[2], h->lw(0, 4), D, F, NL, stride, h->a_sw32);
-    ok = ok && make_tmap_bf16_3d(&h->tm3[3], h->lw(0, 5), D, F, NL, stride, h->a_sw32);
-    ok = ok && make_tmap_bf16_3d(&h->tm3[4], h->lw(0, 6), F, D, NL, stride, h->a_sw32);
-    ok = ok && make_tmap_bf16_3d(&h->tm3[5], h->w(4), D, V, 1, (uint64_t)V * D * 2, h->a_sw32);
-    h->pm[0] = plan_pc(3 * D, D, h->n_sm);
-    h->pm[1] = plan_pc(D, D, h->n_sm);
-    h->pm[2] = plan_pc(2 * F, D, h->n_sm);
-    h->pm[3] = plan_pc(D, F, h->n_sm);
-    h->pm[4] = plan_pc(V, D, h->n_sm);
-    for (int i = 0; i < 5; ++i) ok = ok && h->pm[i].S > 0;
-    ok = ok && (F % 128 == 0) && (D % 128 == 0);
+    for (int wbv = 0; wbv < 2; ++wbv) {
+      const int rows = wbv ? 256 : 128;
+      bool okv = ok;
+      okv = okv && make_tmap_bf16_3d(&h->tm3[wbv][0], h->lw(0, 1), D, 3 * D, NL, stride, rows);
+      okv = okv && make_tmap_bf16_3d(&h->tm3[wbv][1], h->lw(0, 2), D, D, NL, stride, rows);
+      okv = okv && make_tmap_bf16_3d(&h->tm3[wbv][2], h->lw(0, 4), D, F, NL, stride, rows);
+      okv = okv && make_tmap_bf16_3d(&h->tm3[wbv][3], h->lw(0, 5), D, F, NL, stride, rows);
+      okv = okv && make_tmap_bf16_3d(&h->tm3[wbv][4], h->lw(0, 6), F, D, NL, stride, rows);
+      okv = okv && make_tmap_bf16_3d(&h->tm3[wbv][5], h->w(4), D, V, 1, (uint64_t)V * D * 2, rows);
+      h->pm[wbv][0] = plan_pc(3 * D, D, h->n_sm, rows);
+      h->pm[wbv][1] = plan_pc(D, D, h->n_sm, rows);
+      h->pm[wbv][2] = plan_pc(2 * F, D, h->n_sm, rows);
+      h->pm[wbv][3] = plan_pc(D, F, h->n_sm, rows);
+      h->pm[wbv][4] = plan_pc(V, D, h->n_sm, rows);
+      for (int i = 0; i < 5; ++i) okv = okv && h->pm[wbv][i].S > 0;
+      okv = okv && (F % rows == 0) && (D % rows == 0);     // w1 | w3 share one tile index space: F must be whole tiles
+      h->pc_ok2[wbv] = okv;
+    }
+    if (!h->pc_ok2[1]) h->wb = false;
+    ok = h->pc_ok2[h->wb ? 1 : 0];
     h->pc_ok = ok;
   }
   // Opt-in shared-memory size is a per-device function attribute: set it for the device this handle lives on
   // (a process may hold engines on several GPUs).
-  CK(cudaFuncSetAttribute(k_decode_persistent<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PcCfg<32>::SMEM));
-  CK(cudaFuncSetAttribute(k_decode_persistent<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PcCfg<16>::SMEM));
-  CK(cudaFuncSetAttribute(k_decode_persistent<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PcCfg<32>::SMEM));
-  CK(cudaFuncSetAttribute(k_decode_persistent<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PcCfg<16>::SMEM));
+#define MVB_PC_ATTR(FP, NBV, WBV)                                                                                   \
+  CK(cudaFuncSetAttribute(k_decode_persistent<FP, NBV, WBV>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                          (int)PcCfg<NBV, WBV>::SMEM))
+  MVB_PC_ATTR(true, 32, false); MVB_PC_ATTR(true, 16, false); MVB_PC_ATTR(false, 32, false); MVB_PC_ATTR(false, 16, false);
+  MVB_PC_ATTR(true, 32, true); MVB_PC_ATTR(true, 16, true); MVB_PC_ATTR(false, 32, true); MVB_PC_ATTR(false, 16, true);
+#undef MVB_PC_ATTR
   CK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
   CK(cudaMallocHost(&h->h_flags, sizeof(int) * 4 * 64));
   guard.h = nullptr;
@@ -530,36 +548,49 @@ static int launch_body_b(mvb_s1* h, cudaStream_t s, int n_utts) {
 
 // ------------------------------------------------------------------------------------------------
 // Path C: one persistent kernel per decode position (decode_persistent.cuh) followed by the sampler.
-static int launch_persistent(mvb_s1* h, cudaStream_t s, int n_utts) {
+static int launch_persistent(mvb_s1* h, cudaStream_t s, int n_utts, int n_steps, bool fused) {
   const mvb_s1_config& c = h->cfg;
+  const int wbv = h->wb ? 1 : 0;
   PcParams p{};
   p.n_layer = c.n_layer; p.D = c.dim; p.F = c.intermediate; p.V = c.vocab; p.H = c.n_head; p.S_max = c.block_size;
-  p.pf_ahead = h->pf_ahead;
-  p.ts = h->pc_ts;
-  p.n_prod = h->pc_nprod;
+  p.n_steps = n_steps; p.fused = fused ? 1 : 0;
+  p.pf_mode = h->pf_mode; p.pf_ahead = h->pf_ahead; p.epi_mode = h->epi_mode;
   p.R = 2 * n_utts; p.n_utts = n_utts; p.kv_fp32 = c.kv_dtype == MVB_KV_FP32; p.eps = c.norm_eps;
-  p.m_qkv = h->pm[0]; p.m_o = h->pm[1]; p.m_w13 = h->pm[2]; p.m_w2 = h->pm[3]; p.m_head = h->pm[4];
+  p.m_qkv = h->pm[wbv][0]; p.m_o = h->pm[wbv][1]; p.m_w13 = h->pm[wbv][2]; p.m_w2 = h->pm[wbv][3]; p.m_head = h->pm[wbv][4];
   p.attn_norm = h->lw(0, 0); p.ffn_norm = h->lw(0, 3); p.out_norm = h->w(3);
   p.layer_stride = h->layer_stride_elems;
   p.tok_emb = h->w(0); p.pos_emb = h->w(1); p.spk_proj = h->wsp<float>(h->L.spk);
   p.x = h->wsp<float>(h->L.c_x); p.qkv = h->wsp<float>(h->L.c_qkv); p.gu = h->wsp<float>(h->L.c_gu);
   p.logits = h->wsp<float>(h->L.logits);
   p.part_o = h->wsp<float>(h->L.c_part_o); p.part_ml = h->wsp<float>(h->L.c_part_ml);
+  p.stat = h->wsp<float>(h->L.c_stat);
+  p.samp_part = h->wsp<float>(h->L.c_samp_part);
+  p.samp_best = h->wsp<unsigned long long>(h->L.c_samp_best);
   p.kv = h->kv; p.kv_half = h->kv_half_bytes();
   p.bar = h->wsp<unsigned>(h->L.c_bar);
   p.trace = (h->trace && h->n_sm <= 160) ? h->wsp<long long>(h->L.c_trace) : nullptr;
   p.st = h->st;
+  // launch-time invariants of the kernel: grid-barrier counter, RMSNorm statistics and arg-max slots start from zero
+  CK(cudaMemsetAsync(p.bar, 0, 4, s));
+  CK(cudaMemsetAsync(p.stat, 0, sizeof(float) * (size_t)(2 * c.n_layer + 1) * PC_RPAD, s));
+  CK(cudaMemsetAsync(p.samp_best, 0, sizeof(unsigned long long) * 2 * (PC_RPAD / 2), s));
   h->launches++;
-  const bool fp = p.kv_fp32 != 0, wide = p.R > PcCfg<16>::RH;
-#define MVB_PC_LAUNCH(FP, NBV, IDX)                                                                                   \
-  do {                                                                                                                \
-    CK(launch_pdl(h->pdl, k_decode_persistent<FP, NBV>, dim3(h->n_sm), dim3(PC_THREADS), PcCfg<NBV>::SMEM, s,         \
-                  h->tm3[0], h->tm3[1], h->tm3[2], h->tm3[3], h->tm3[4], h->tm3[5], p));                              \
-  } while (0)
-  if (fp && wide) MVB_PC_LAUNCH(true, 32, 0);
-  else if (fp) MVB_PC_LAUNCH(true, 16, 1);
-  else if (wide) MVB_PC_LAUNCH(false, 32, 2);
-  else MVB_PC_LAUNCH(false, 16, 3);
+  const bool fp = p.kv_fp32 != 0, wide = p.R > 8;
+  const CUtensorMap* tm = h->tm3[wbv];
+#define MVB_PC_LAUNCH(FP, NBV, WBV)                                                                                   \
+  CK(launch_pdl(h->pdl, k_decode_persistent<FP, NBV, WBV>, dim3(h->n_sm), dim3(PC_THREADS), PcCfg<NBV, WBV>::SMEM, s, \
+                tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p))
+  if (wbv) {
+    if (fp && wide) MVB_PC_LAUNCH(true, 32, true);
+    else if (fp) MVB_PC_LAUNCH(true, 16, true);
+    else if (wide) MVB_PC_LAUNCH(false, 32, true);
+    else MVB_PC_LAUNCH(false, 16, true);
+  } else {
+    if (fp && wide) MVB_PC_LAUNCH(true, 32, false);
+    else if (fp) MVB_PC_LAUNCH(true, 16, false);
+    else if (wide) MVB_PC_LAUNCH(false, 32, false);
+    else MVB_PC_LAUNCH(false, 16, false);
+  }
 #undef MVB_PC_LAUNCH
   return MVB_OK;
 }
@@ -697,6 +728,7 @@ extern "C" int mvb_s1_begin(mvb_s1* h, int32_t utt, int32_t first_token, int32_t
   if (!h || !p) return fail(MVB_ERR_ARG, "null argument");
   if (utt < 0 || utt >= h->cfg.max_utts) return fail(MVB_ERR_ARG, "utterance slot %d out of range", utt);
   if (pos < 0 || pos >= h->cfg.block_size) return fail(MVB_ERR_ARG, "position %d outside the context", pos);
+  h->h_topk[utt] = p->top_k;
   k_begin<<<1, 32, 0, (cudaStream_t)stream>>>(h->st, utt, first_token, pos, to_dev(p), d_noise, d_forced, first_token >= 0,
                                               h->cfg.max_new);
   h->launches++;
@@ -726,6 +758,7 @@ static int sample_step(mvb_s1* h, cudaStream_t s, int n_utts) {
 extern "C" int mvb_s1_decode(mvb_s1* h, int32_t n_utts, int32_t n_steps, void* stream) {
   if (!h) return fail(MVB_ERR_ARG, "null handle");
   if (n_utts < 1 || n_utts > h->cfg.max_utts) return fail(MVB_ERR_ARG, "n_utts %d out of range", n_utts);
+  if (n_steps < 1) return MVB_OK;
   cudaStream_t s = (cudaStream_t)stream;
   k_identity_slots<<<1, 64, 0, s>>>(h->st, n_utts);
   h->launches++;
@@ -733,12 +766,18 @@ extern "C" int mvb_s1_decode(mvb_s1* h, int32_t n_utts, int32_t n_steps, void* s
   const bool use_c = h->path_c && h->pc_ok && 2 * n_utts <= PC_RPAD;
   if (use_c) {
     // The persistent kernel ACCUMULATES split-K partial logits (red.add); a prefill (mvb_s1_forward) leaves the last
-    // position's logits in the same rows, so they must be zero before the first fused step.
+    // position's logits in the same rows, so they must be zero before the first fused step.  Its grid-barrier counter
+    // starts from zero at every launch.
     CK(cudaMemsetAsync(h->wsp<float>(h->L.logits), 0, sizeof(float) * 2 * (size_t)n_utts * h->cfg.vocab, s));
+    // One launch for the whole burst: the kernel samples on the device (top_k = None only, the stage-1 default of
+    // TTS.synthesise) and stays resident across positions.
+    bool fused = h->fused && (h->cfg.vocab + h->n_sm - 1) / h->n_sm <= PC_SAMP_OWN && h->cfg.vocab <= SAMP_PAD;
+    for (int u = 0; u < n_utts; ++u) fused = fused && h->h_topk[u] <= 0;
+    if (fused) return launch_persistent(h, s, n_utts, n_steps, true);
   }
   for (int i = 0; i < n_steps; ++i) {
     if (use_c) {
-      if (int e = launch_persistent(h, s, n_utts)) return e;
+      if (int e = launch_persistent(h, s, n_utts, 1, false)) return e;   // (the sampler below resets the barrier counter)
     } else {
       if (int e = run_body(h, s, n_utts)) return e;
     }
@@ -762,7 +801,7 @@ extern "C" int mvb_s1_step_logits(mvb_s1* h, int32_t n_utts, float* d_logits, vo
   CK(cudaGetLastError());
   CK(cudaMemsetAsync(h->wsp<float>(h->L.logits), 0, bytes, s));
   CK(cudaMemsetAsync(h->wsp<unsigned>(h->L.c_bar), 0, 4, s));
-  if (int e = launch_persistent(h, s, n_utts)) return e;
+  if (int e = launch_persistent(h, s, n_utts, 1, false)) return e;
   CK(cudaMemcpyAsync(d_logits, h->wsp<float>(h->L.logits), bytes, cudaMemcpyDeviceToDevice, s));
   CK(cudaMemsetAsync(h->wsp<float>(h->L.logits), 0, bytes, s));
   CK(cudaMemsetAsync(h->wsp<unsigned>(h->L.c_bar), 0, 4, s));

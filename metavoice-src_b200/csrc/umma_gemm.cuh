@@ -74,7 +74,9 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmB, const GemmP p) {
   constexpr int NA = (EPI == G_SWIGLU) ? 2 : 1;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by POINTER ARITHMETIC on the shared array: an integer round trip would lose the .shared state
+  // space and turn every access below into a generic LD/ST (higher latency, no LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int S = p.stages;
   const int b_bytes = p.NB * 128;
   const int stage_bytes = NA * GEMM_A_BYTES + b_bytes;

@@ -18,16 +18,36 @@ from typing import Dict
 
 import torch
 
-REFERENCE_ROOT = os.environ.get("MVB_REFERENCE_ROOT", "/root/reference")
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _resolve_root() -> str:
+    """/root/reference in the build container; on the GPU box the byte-identical copy oracle/build_ref.py made
+    (oracle/_ref, git-ignored, travels with the snapshot)."""
+    env = os.environ.get("MVB_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/fam/llm"):
+        return "/root/reference"
+    return _VENDORED
+
+
+REFERENCE_ROOT = _resolve_root()
 
 
 def available() -> bool:
+    """The reference tree itself is mounted (build container): gates the live-reference tests."""
+    return os.path.isdir("/root/reference/fam/llm") or bool(os.environ.get("MVB_REFERENCE_ROOT"))
+
+
+def runnable() -> bool:
+    """The reference's code can be imported here (mounted tree or the vendored copy): gates bench.py's reference arm."""
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "fam", "llm"))
 
 
 def _import_reference():
-    if not available():
-        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    if not runnable():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT} (run oracle/build_ref.py in the build container)")
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     if "librosa" not in sys.modules:

@@ -1,5 +1,7 @@
-"""Decode-step time (CUDA events, graph replays) for several engine configurations in one process.
-Usage: python tools/step_time.py "A1:1,A0:1,B:1,B:2,B:4,B:8"   (A1 = CUDA-core path with PDL, A0 = without, B = tensor-core path)"""
+"""Decode-step time (CUDA events) for several engine configurations in one process.
+Usage: python tools/step_time.py "A1:1,B:8,C:1,C:1:MVB_PC_WB=0+MVB_PF_MODE=2+MVB_PF_AHEAD=16,C:8" [context_len]
+  A1 = CUDA-core path with PDL, A0 = without, B = tensor-core rows path, C = persistent fused kernel;
+  second field = utterances; optional third field = '+'-separated environment switches read by mvb_s1_create."""
 import ctypes as C
 import json
 import os
@@ -27,12 +29,13 @@ res = []
 for item in spec.split(","):
     parts = item.split(":")
     kind, n = parts[0], int(parts[1])
-    os.environ["MVB_PF_AHEAD"] = parts[2] if len(parts) > 2 else "0"
-    os.environ["MVB_PC_NPROD"] = parts[3] if len(parts) > 3 else "1"
+    extra = dict(kv.split("=") for kv in parts[2].split("+")) if len(parts) > 2 and parts[2] else {}
+    for k in ("MVB_PC_WB", "MVB_PC_FUSED", "MVB_PF_MODE", "MVB_PF_AHEAD", "MVB_PC_EPI"):
+        os.environ.pop(k, None)
+    os.environ.update(extra)
     os.environ["MVB_PDL"] = "0" if kind.endswith("0") else "1"
     os.environ["MVB_DECODE_B_MIN"] = "1" if kind.startswith("B") else "9999"
     os.environ["MVB_PATHC"] = "1" if kind[0] in "CS" else "0"
-    os.environ["MVB_A_SW32"] = "1" if kind.startswith("S") else "0"
     m = Transformer(cfg, arena, offsets, device=dev)
     m.setup_caches(2 * n, cfg.block_size, kv_dtype="bf16")
     lib, h, st = m._lib, m.handle, m._stream()

@@ -16,6 +16,9 @@ from mvb200.fast_model import ModelArgs, Transformer, pack_arena  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 L_mid = int(sys.argv[2]) if len(sys.argv) > 2 else 423
+for kv in (sys.argv[3].split("+") if len(sys.argv) > 3 and sys.argv[3] else []):   # e.g. MVB_PC_WB=0+MVB_PF_MODE=2
+    k, v = kv.split("=")
+    os.environ[k] = v
 dev = torch.device("cuda:0"); torch.cuda.set_device(dev)
 d = synth.FULL
 cfg = ModelArgs.from_name("metavoice-1B")
