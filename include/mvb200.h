@@ -121,6 +121,20 @@ int mvb_s1_generate(mvb_s1* h, int32_t n_utts, const int32_t* prompts, const int
  * a host sync.  Used by bench.py for the HBM-resident `value` and by the shim's generate(). */
 int mvb_s1_decode(mvb_s1* h, int32_t n_utts, int32_t n_steps, void* stream);
 
+/* Continuous batching (the reference serialises requests, serving.py:59-109): utterances enter and
+ * leave KV slots between decode bursts of the persistent kernel.
+ *   mvb_s1_admit   == the per-utterance prologue of generate() (utils:196-212) for slot `utt`: HOST prompt int32 [T] and
+ *                  speaker vector fp32 [spk_dim] are uploaded, the prompt is prefilled and the first token is sampled;
+ *                  d_noise: optional DEVICE Exp(1) draws [max_new_tokens, vocab] (NULL = on-device Philox, params->seed).
+ *                  Returns MVB_ERR_PROMPT_TOO_LONG like generate().
+ *   mvb_s1_decode  then advances every slot [0, n_slots) by a burst; finished / parked slots are skipped by the sampler.
+ *   mvb_s1_poll    done flags + generated-token counts of slots [0, n_slots) (one device->host round trip).
+ *   mvb_s1_release parks a slot (done latch set) until the next admit. */
+int mvb_s1_admit(mvb_s1* h, int32_t utt, const int32_t* prompt, int32_t T, const float* spk_emb,
+                 const mvb_sampling* params, int32_t max_new_tokens, const float* d_noise, void* stream);
+int mvb_s1_release(mvb_s1* h, int32_t utt, void* stream);
+int mvb_s1_poll(mvb_s1* h, int32_t n_slots, int32_t* done_out, int32_t* n_gen_out, void* stream);
+
 /* Install per-utterance decode state after prefill: first token, sampling params, optional device
  * noise [max_new, vocab] / forced-token [max_new] buffers (NULL = none). */
 int mvb_s1_begin(mvb_s1* h, int32_t utt, int32_t first_token, int32_t pos, const mvb_sampling* p,
@@ -218,6 +232,48 @@ int mvb_voc_destroy(mvb_voc* h);
 int mvb_voc_decode_latent(mvb_voc* h, const int32_t* d_codes, int32_t T, float* d_latent, void* stream);
 /* d_codes int32 [n_q, T] -> d_wav fp32 [T * prod(ratios)]  (EncodecModel.decode, one chunk, 24 kHz) */
 int mvb_voc_decode(mvb_voc* h, const int32_t* d_codes, int32_t T, float* d_wav, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Speaker encoder: fam/quantiser/audio/speaker_encoder/{audio.py:10-22, model.py:50-103}.
+ * 16 kHz mono fp32 waveform -> power mel spectrogram (n_fft 400, hop 160, 40 Slaney bands, centered, zero padded) ->
+ * 3-layer LSTM(40 -> 256) over partial windows of 160 frames -> linear -> ReLU -> L2 norm -> mean -> L2 norm. */
+typedef struct mvb_spk_config {
+  int32_t n_mels;          /* 40 */
+  int32_t hidden;          /* 256 */
+  int32_t n_layers;        /* 3 */
+  int32_t emb;             /* 256 */
+  int32_t n_fft;           /* 400 = 25 ms at 16 kHz */
+  int32_t hop;             /* 160 = 10 ms */
+  int32_t partial_frames;  /* 160 */
+  int32_t max_samples;     /* workspace capacity (samples at 16 kHz) */
+} mvb_spk_config;
+typedef struct mvb_spk mvb_spk;
+/* fp32 arena tensors, in this order: per LSTM layer {weight_ih [4H, in], weight_hh [4H, H], bias_ih + bias_hh [4H]},
+ * linear.weight [256, 256], linear.bias [256], mel filterbank [n_mels, n_fft/2 + 1], analysis window [n_fft],
+ * cos(2 pi i / n_fft) [n_fft], -sin(2 pi i / n_fft) [n_fft]. */
+#define MVB_SPK_TENSORS 15
+size_t mvb_spk_workspace_bytes(const mvb_spk_config* cfg);
+int mvb_spk_create(const mvb_spk_config* cfg, const void* d_arena, size_t arena_bytes, const uint64_t* offsets,
+                   void* d_workspace, mvb_spk** out);
+int mvb_spk_destroy(mvb_spk* h);
+/* == audio.wav_to_mel_spectrogram: d_wav fp32 [n_samples] -> d_mel fp32 [1 + n_samples / hop, n_mels] (parity hook). */
+int mvb_spk_mel(mvb_spk* h, const float* d_wav, int32_t n_samples, float* d_mel, void* stream);
+/* == SpeakerEncoder.embed_utterance on an already padded waveform: slice_starts (HOST int32 [n_partials]) are the first mel
+ * frames of the partial windows (compute_partial_slices, model.py:55-79); d_embed fp32 [256]; d_partials_out optional
+ * fp32 [n_partials, 256]. */
+int mvb_spk_embed(mvb_spk* h, const float* d_wav, int32_t n_samples, const int32_t* slice_starts, int32_t n_partials,
+                  float* d_embed, float* d_partials_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Audio post-processing on the device == `_save_audio` (fam/llm/decoders.py:40-47 -> audiocraft
+ * audio_write(strategy="loudness", loudness_compressor=True)): BS.1770-4 integrated loudness exactly as
+ * torchaudio.functional.loudness computes it (the function audiocraft calls), gain to -loudness_headroom_db LUFS, tanh
+ * compressor, clip, PCM16.  d_wav fp32 mono [n_samples]; d_pcm16 int16 [n_samples]; d_wav_out optional fp32 [n_samples];
+ * d_lkfs_gain optional fp32 [2] = {measured LKFS, applied linear gain}.  Signals below the 2e-3 RMS floor pass through. */
+size_t mvb_audio_post_workspace_bytes(int32_t max_samples);
+int mvb_audio_post(const float* d_wav, int32_t n_samples, int32_t sample_rate, float loudness_headroom_db,
+                   int32_t loudness_compressor, void* d_workspace, int16_t* d_pcm16, float* d_wav_out,
+                   float* d_lkfs_gain, void* stream);
 
 #define MVB_OK 0
 #define MVB_ERR_CUDA 1

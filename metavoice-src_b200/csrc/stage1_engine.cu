@@ -743,6 +743,67 @@ __global__ void k_set_budget(S1State st, int utt, int budget) {
 __global__ void k_set_noise_base(S1State st, int n_utts, int base) {
   if ((int)threadIdx.x < n_utts) st.noise_base[threadIdx.x] = base;
 }
+__global__ void k_set_done(S1State st, int utt, int done) {
+  if (threadIdx.x == 0) st.done[utt] = done;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Continuous batching: utterances enter and leave KV slots between decode bursts.
+// mvb_s1_admit == the per-utterance prologue of generate() (utils:196-212): budget check, prompt / speaker upload,
+// prefill, first token sampled from the last prompt position.  The slot then rides along in every mvb_s1_decode burst
+// until its done flag latches (mvb_s1_poll), after which the host fetches its tokens and may admit another request.
+extern "C" int mvb_s1_admit(mvb_s1* h, int32_t utt, const int32_t* prompt, int32_t T, const float* spk_emb,
+                            const mvb_sampling* params, int32_t max_new_tokens, const float* d_noise, void* stream) {
+  if (!h || !prompt || !spk_emb || !params) return fail(MVB_ERR_ARG, "null argument");
+  const mvb_s1_config& c = h->cfg;
+  if (utt < 0 || utt >= c.max_utts) return fail(MVB_ERR_ARG, "utterance slot %d out of range", utt);
+  if (T < 1) return fail(MVB_ERR_ARG, "empty prompt");
+  if (max_new_tokens < 1 || max_new_tokens > c.max_new) return fail(MVB_ERR_ARG, "max_new_tokens %d out of range", max_new_tokens);
+  const int room = (T + max_new_tokens < c.block_size ? T + max_new_tokens : c.block_size) - T;
+  if (room <= 0) return fail(MVB_ERR_PROMPT_TOO_LONG, "Prompt is too long to generate more tokens");
+  cudaStream_t s = (cudaStream_t)stream;
+  int* di = h->wsp<int>(h->L.stage_idx) + (size_t)utt * 2 * c.block_size;
+  float* d_spk = h->wsp<float>(h->L.stage_spk) + (size_t)utt * c.spk_dim;
+  CK(cudaMemcpyAsync(d_spk, spk_emb, sizeof(float) * c.spk_dim, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(di, prompt, sizeof(int) * T, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(di + T, prompt, sizeof(int) * T, cudaMemcpyHostToDevice, s));
+  if (int e = mvb_s1_set_speaker(h, utt, d_spk, s)) return e;
+  if (int e = mvb_s1_begin(h, utt, -1, 0, params, d_noise, nullptr, s)) return e;
+  k_set_budget<<<1, 32, 0, s>>>(h->st, utt, room);
+  h->launches++;
+  if (int e = mvb_s1_forward(h, utt, di, T, 0, nullptr, 0, s)) return e;
+  SampleP spp{};
+  spp.logits = h->wsp<float>(h->L.logits);
+  spp.V = c.vocab;
+  spp.decode_mode = 1;
+  k_sample<<<1, SAMP_THREADS, 0, s>>>(spp, h->st);  // slot_map[0] == utt after the prefill
+  h->launches++;
+  CK(cudaGetLastError());
+  return MVB_OK;
+}
+
+// Park a slot: its rows still ride along in the batch (recomputed at a frozen position) but nothing is sampled or
+// appended for it until the next mvb_s1_admit / mvb_s1_begin.
+extern "C" int mvb_s1_release(mvb_s1* h, int32_t utt, void* stream) {
+  if (!h) return fail(MVB_ERR_ARG, "null handle");
+  if (utt < 0 || utt >= h->cfg.max_utts) return fail(MVB_ERR_ARG, "utterance slot %d out of range", utt);
+  k_set_done<<<1, 32, 0, (cudaStream_t)stream>>>(h->st, utt, 1);
+  h->launches++;
+  CK(cudaGetLastError());
+  return MVB_OK;
+}
+
+// done flags and generated-token counts of slots [0, n_slots) in one device->host round trip (synchronises `stream`).
+extern "C" int mvb_s1_poll(mvb_s1* h, int32_t n_slots, int32_t* done_out, int32_t* n_gen_out, void* stream) {
+  if (!h || !done_out || !n_gen_out) return fail(MVB_ERR_ARG, "null argument");
+  if (n_slots < 1 || n_slots > h->cfg.max_utts) return fail(MVB_ERR_ARG, "n_slots %d out of range", n_slots);
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(h->h_flags, h->st.done, sizeof(int) * n_slots, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(h->h_flags + 64, h->st.n_gen, sizeof(int) * n_slots, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  for (int i = 0; i < n_slots; ++i) { done_out[i] = h->h_flags[i]; n_gen_out[i] = h->h_flags[64 + i]; }
+  return MVB_OK;
+}
 
 static int sample_step(mvb_s1* h, cudaStream_t s, int n_utts) {
   SampleP sp{};

@@ -37,6 +37,11 @@ class VocConfig(C.Structure):
                 ("compress", C.c_int32), ("max_frames", C.c_int32)]
 
 
+class SpkConfig(C.Structure):
+    _fields_ = [("n_mels", C.c_int32), ("hidden", C.c_int32), ("n_layers", C.c_int32), ("emb", C.c_int32), ("n_fft", C.c_int32),
+                ("hop", C.c_int32), ("partial_frames", C.c_int32), ("max_samples", C.c_int32)]
+
+
 # name -> (restype, argtypes); also the list the symbol-export test checks against include/mvb200.h
 SIGNATURES = {
     "mvb_abi_version": (C.c_int, []),
@@ -58,6 +63,10 @@ SIGNATURES = {
                                C.c_void_p, C.c_void_p]),
     "mvb_s1_fetch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32),
                                C.POINTER(C.c_int32), C.c_void_p]),
+    "mvb_s1_admit": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(Sampling), C.c_int32,
+                               C.c_void_p, C.c_void_p]),
+    "mvb_s1_release": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "mvb_s1_poll": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mvb_s1_step_logits": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "mvb_s1_launch_count": (C.c_uint64, [C.c_void_p]),
     "mvb_s2_workspace_bytes": (C.c_size_t, [C.POINTER(S2Config)]),
@@ -72,6 +81,15 @@ SIGNATURES = {
     "mvb_voc_destroy": (C.c_int, [C.c_void_p]),
     "mvb_voc_decode_latent": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "mvb_voc_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mvb_spk_workspace_bytes": (C.c_size_t, [C.POINTER(SpkConfig)]),
+    "mvb_spk_create": (C.c_int, [C.POINTER(SpkConfig), C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.c_void_p,
+                                 C.POINTER(C.c_void_p)]),
+    "mvb_spk_destroy": (C.c_int, [C.c_void_p]),
+    "mvb_spk_mel": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mvb_spk_embed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mvb_audio_post_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "mvb_audio_post": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p]),
     "mvb_linear": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_float,
                              C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     # test / debug hooks (declared in the header as such)

@@ -71,3 +71,38 @@ def read_wav_pcm16(path: str):
     n = struct.unpack("<I", b[40:44])[0]
     x = np.frombuffer(b[44:44 + n], dtype="<i2").reshape(-1, ch).T.astype(np.float32) / 32767.0
     return torch.from_numpy(x.copy()), sr
+
+
+# ---- on-device variant: loudness meter, gain, compressor and PCM16 conversion in libmvb200 -----------
+_POST_WS = {}
+
+
+def wav_bytes_on_device(wav: torch.Tensor, sample_rate: int, loudness_headroom_db: float = LOUDNESS_HEADROOM_DB,
+                        loudness_compressor: bool = True, return_stats: bool = False):
+    """Device fp32 mono waveform [T] (or [1, T]) -> the bytes of the wav FILE `_save_audio` would have written
+    (decoders.py:40-47): only 2 bytes per sample cross the PCIe bus, no temp file (serving.py:96-97 re-reads the file it
+    just wrote; a server can return these bytes directly)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    w = wav.detach().reshape(-1).to(torch.float32).contiguous()
+    assert w.is_cuda, "wav_bytes_on_device expects a device tensor (use audio_write_wav for host tensors)"
+    n = w.numel()
+    key = (w.device, max(n, 1 << 17))
+    ws = _POST_WS.get(w.device)
+    if ws is None or ws[0] < n:
+        cap = max(n, 1 << 20)
+        ws = (cap, torch.empty(lib.mvb_audio_post_workspace_bytes(cap), dtype=torch.uint8, device=w.device))
+        _POST_WS[w.device] = ws
+    pcm = torch.empty(n, dtype=torch.int16, device=w.device)
+    stats = torch.empty(2, dtype=torch.float32, device=w.device)
+    st = C.c_void_p(torch.cuda.current_stream(w.device).cuda_stream)
+    _lib.check(lib.mvb_audio_post(w.data_ptr(), n, int(sample_rate), float(loudness_headroom_db), int(bool(loudness_compressor)),
+                                  ws[1].data_ptr(), pcm.data_ptr(), None, stats.data_ptr(), st))
+    body = pcm.cpu().numpy().astype("<i2").tobytes()
+    header = (b"RIFF" + struct.pack("<I", 36 + len(body)) + b"WAVEfmt " +
+              struct.pack("<IHHIIHH", 16, 1, 1, sample_rate, sample_rate * 2, 2, 16) + b"data" + struct.pack("<I", len(body)))
+    if return_stats:
+        lk, gain = stats.cpu().tolist()
+        return header + body, lk, gain
+    return header + body

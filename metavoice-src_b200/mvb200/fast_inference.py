@@ -3,17 +3,18 @@
 Same constructor keywords and the same ``synthesise(text, spk_ref_path, top_p, guidance_scale, temperature) -> path``
 contract (fast_inference.py:41-50, 111-119, 195).  Differences, all stated where they occur:
   * checkpoints are read from a local directory (the reference calls ``snapshot_download``, :71; no network here);
-  * the speaker vector must already exist (``.pt`` tensor / ``.npy``) -- the LSTM speaker encoder runs once per
-    speaker and is disk-cached by the reference (inference.py:419-435); it is outside the hot path (SURVEY.md N3);
+  * the speaker reference may be a RIFF/WAVE file (>= 30 s, utils.py:55-70), embedded by the on-device speaker encoder
+    (mvb200/speaker_encoder.py) and disk-cached like the reference (inference.py:419-435), or an already
+    computed embedding (``.pt`` tensor / ``.npy``); mp3 / flac / URLs need a decoder / network that this image lacks;
   * the vocoder stage is the EnCodec decoder; the multi-band-diffusion refinement and the DeepFilterNet enhancer
     (decoders.py:85, fast_inference.py:158-163) are not implemented (unpinned third-party code, SURVEY.md §8c / N1);
-  * the wav is written as plain PCM16 (the reference's ``audio_write`` also loudness-normalises, decoders.py:40-47; N2).
+  * the wav goes through the reference's ``audio_write`` post-processing (loudness normalisation to -14 LUFS, tanh
+    compressor, PCM16; decoders.py:40-47) in mvb200/audio_out.py.
 """
 from __future__ import annotations
 
 import os
 import re
-import struct
 import time
 import uuid
 from datetime import datetime
@@ -46,24 +47,19 @@ def normalize_text(text: str) -> str:
     return re.sub(r"\s\s+", " ", text)
 
 
-def write_wav_pcm16(path: str, wav: np.ndarray, sample_rate: int) -> None:
-    pcm = (np.clip(wav, -1.0, 1.0) * 32767.0).astype("<i2").tobytes()
-    with open(path, "wb") as f:
-        f.write(b"RIFF" + struct.pack("<I", 36 + len(pcm)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 1, sample_rate,
-                                                                                       sample_rate * 2, 2, 16))
-        f.write(b"data" + struct.pack("<I", len(pcm)) + pcm)
-
-
-def load_speaker_embedding(path: str) -> torch.Tensor:
+def load_speaker_embedding(path: str, smodel=None) -> torch.Tensor:
     if not os.path.exists(path):
-        raise FileNotFoundError(f"File {path} not found!")      # inference.py:420-421
+        raise FileNotFoundError(f"File {path} not found!")      # inference.py:412-415, 420-421
     if path.endswith(".npy"):
         e = torch.from_numpy(np.load(path))
     elif path.endswith(".pt"):
         e = torch.load(path, map_location="cpu")
     else:
-        raise NotImplementedError("speaker reference must be a precomputed embedding (.pt / .npy): the speaker encoder "
-                                  "is outside the accelerated path (SURVEY.md row N3)")
+        if smodel is None:
+            raise FileNotFoundError("speaker_encoder.pt not found in the model directory: pass a precomputed embedding (.pt / .npy)")
+        from .speaker_encoder import check_audio_file, get_cached_embedding
+        check_audio_file(path)                                  # fast_inference.py:123: >= 30 s of reference audio
+        e = get_cached_embedding(path, smodel)                  # fast_inference.py:124-127
     return e.reshape(1, -1).float()
 
 
@@ -72,7 +68,7 @@ class TTS:
 
     def __init__(self, model_name: str = "metavoiceio/metavoice-1B-v0.1", *, seed: int = 1337, output_dir: str = "outputs",
                  quantisation_mode: Optional[Literal["int4", "int8"]] = None, first_stage_path: Optional[str] = None,
-                 telemetry_origin: Optional[str] = None, encodec_state_dict=None, device: str = "cuda"):
+                 telemetry_origin: Optional[str] = None, encodec_state_dict=None, device: str = "cuda", max_utts: int = 1):
         self._device = device
         self._model_dir = model_name
         if not os.path.isdir(model_name):
@@ -92,12 +88,16 @@ class TTS:
         self.model, self.tokenizer, self.smodel, self.model_size = build_model(
             precision=self.precision, checkpoint_path=Path(self._first_stage_ckpt),
             spk_emb_ckpt_path=Path(f"{self._model_dir}/speaker_encoder.pt"), device=device, compile=True,
-            compile_prefill=True, quantisation_mode=quantisation_mode)
+            compile_prefill=True, quantisation_mode=quantisation_mode, max_utts=max_utts)
         self._seed = seed
+        spk_ckpt = f"{self._model_dir}/speaker_encoder.pt"
+        if os.path.isfile(spk_ckpt):                                                   # fast_inference_utils.py:314-318
+            from .speaker_encoder import SpeakerEncoder
+            self.smodel = SpeakerEncoder(weights_fpath=spk_ckpt, device=device, eval=True, verbose=False)
 
     def synthesise(self, text: str, spk_ref_path: str, top_p=0.95, guidance_scale=3.0, temperature=1.0) -> str:
         text = normalize_text(text)
-        spk_emb = load_speaker_embedding(spk_ref_path)
+        spk_emb = load_speaker_embedding(spk_ref_path, self.smodel)
         start = time.time()
         tokens = main(model=self.model, tokenizer=self.tokenizer, model_size=self.model_size, prompt=text, spk_emb=spk_emb,
                       top_p=top_p, guidance_scale=guidance_scale, temperature=temperature, device=self._device)
@@ -117,4 +117,38 @@ class TTS:
         dur = wav.shape[-1] / 24000.0
         print(f"\nTotal time to synth (s): {dt}")
         print(f"Real-time factor: {dt / dur:.2f}")
+        return path
+
+    def synthesise_long(self, text: str, spk_ref_path: str, top_p=0.95, guidance_scale=3.0, temperature=1.0,
+                        max_chars: int = 220) -> str:
+        """Long-form synthesis (the reference truncates at 220 characters, inference.py:535-541: "Long form synthesis
+        coming soon"): the text is cut into <= ``max_chars`` chunks at sentence boundaries, the chunks are decoded as one
+        continuous batch over the engine's KV slots (``TTS(max_utts=...)``), every chunk goes through stage 2 and the
+        vocoder, and the waveforms are concatenated into one file."""
+        from .fast_inference_utils import encode_tokens
+        from .serving import ContinuousBatcher, chunk_text
+        chunks = chunk_text(normalize_text(text), max_chars)
+        if not chunks:
+            raise ValueError("empty text")
+        spk_emb = load_speaker_embedding(spk_ref_path, self.smodel)
+        start = time.time()
+        cb = ContinuousBatcher(self.model)
+        ids = [cb.submit(encode_tokens(self.tokenizer, c, device="cpu"), spk_emb, top_p=top_p, guidance_scale=guidance_scale,
+                         temperature=temperature) for c in chunks]
+        toks = cb.run_until_done()
+        wavs = []
+        for c, rid in zip(chunks, ids):
+            _, extracted = flattened_interleaved_decode(toks[rid].tolist(), self.END_OF_AUDIO_TOKEN)
+            codes = self.llm_second_stage.non_causal_sample(
+                texts=[c], encodec_tokens=[torch.tensor(extracted, dtype=torch.int32).unsqueeze(0)],
+                speaker_embs=spk_emb.unsqueeze(0), batch_size=1, top_k=200, temperature=1.0)[0]
+            wavs.append(self.codec.decode(codes).reshape(-1))
+        wav = torch.cat(wavs)
+        if wav.shape[-1] < 9600:
+            raise Exception("wav predicted is shorter than 400ms!")                    # decoders.py:88-91
+        name = f"synth_{datetime.now().strftime('%y-%m-%d--%H-%M-%S')}_{chunks[0].replace(' ', '_')[:25]}_{uuid.uuid4()}"
+        path = audio_write_wav(str(Path(self.output_dir).resolve() / name), wav.reshape(1, -1), 24000,
+                               strategy="loudness", loudness_compressor=True)
+        dt = time.time() - start
+        print(f"\nSaved audio to {path} ({len(chunks)} chunks, {wav.shape[-1] / 24000.0:.1f} s of audio in {dt:.2f} s)")
         return path

@@ -267,3 +267,34 @@ def encodec_model_and_state_dict(seed: int = 0):
         for q in m.quantizer.layers:           # codebooks are zero-initialised buffers: give them content
             q.codebook.embed.normal_(0.0, 1.0)
     return m, {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def speaker_encoder_state_dict(seed: int = 3) -> Dict[str, torch.Tensor]:
+    """``speaker_encoder.pt["model_state"]`` layout (fam/quantiser/audio/speaker_encoder/model.py:30-32, 45-46):
+    ``nn.LSTM(40, 256, 3, batch_first=True)`` + ``nn.Linear(256, 256)``, torch's default U(-1/sqrt(H), 1/sqrt(H)) init."""
+    gen = torch.Generator().manual_seed(seed)
+    H, k = 256, 1.0 / 16.0
+    u = lambda *shape: (torch.rand(*shape, generator=gen) * 2 - 1) * k
+    sd: Dict[str, torch.Tensor] = {}
+    for l in range(3):
+        sd[f"lstm.weight_ih_l{l}"] = u(4 * H, 40 if l == 0 else H)
+        sd[f"lstm.weight_hh_l{l}"] = u(4 * H, H)
+        sd[f"lstm.bias_ih_l{l}"] = u(4 * H)
+        sd[f"lstm.bias_hh_l{l}"] = u(4 * H)
+    sd["linear.weight"] = u(H, H)
+    sd["linear.bias"] = u(H).abs()          # keeps a healthy fraction of the ReLU outputs alive
+    return sd
+
+
+def synthetic_waveform(seconds: float, sr: int, seed: int = 5):
+    """Deterministic speech-like test signal (sum of drifting harmonics + noise bursts), float32 in [-1, 1]."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    n = int(seconds * sr)
+    t = np.arange(n) / sr
+    f0 = 110 + 40 * np.sin(2 * np.pi * 0.7 * t) + 15 * np.sin(2 * np.pi * 3.1 * t)
+    phase = 2 * np.pi * np.cumsum(f0) / sr
+    sig = sum((0.5 ** h) * np.sin((h + 1) * phase + rng.uniform(0, 6.28)) for h in range(6))
+    env = 0.5 * (1 + np.sin(2 * np.pi * 2.3 * t)) * (0.6 + 0.4 * np.sin(2 * np.pi * 0.31 * t + 1.0))
+    sig = sig * env + 0.02 * rng.standard_normal(n)
+    return (0.3 * sig / np.abs(sig).max()).astype(np.float32)
