@@ -358,18 +358,25 @@ def main():
 
 
 def pipeline_leg(model, prompts, spk, h_spk_pinned, utts, steps, device, world, barrier):
-    """stage-1 -> adapters -> stage-2 -> vocoder -> wav on host, audio-seconds per second with per-stage milliseconds."""
-    from mvb200 import synth, fast_inference_utils as U
+    """Host text-side inputs -> wav BYTES on the host: stage-1 -> adapters -> stage-2 -> EnCodec decoder -> multi-band
+    diffusion (parametrised config, parity unpinned) -> on-device loudness normalisation / compressor / PCM16.  Reports
+    audio-seconds per second with per-stage milliseconds; DeepFilterNet (fast_inference.py:158-163) is NOT implemented."""
+    from mvb200 import audio_out as A, synth, fast_inference_utils as U
+    from mvb200.mbd import MBDSettings, MultiBandDiffusionEngine
     from mvb200.second_stage import SecondStage, flattened_interleaved_decode
     from mvb200.vocoder import EncodecDecodeEngine
     s2 = SecondStage(synth.stage2_checkpoint(synth.S2_FULL, 1), device=device, max_batch=1)
     codec = EncodecDecodeEngine(synth.encodec_model_and_state_dict(0)[1], device=device, max_frames=1024)
+    mbd_cfg = MBDSettings()                 # hidden 48, depth 4, growth 4, k 8 / s 4, 4 band models x 20 calls, 32-band re-EQ
+    mbd = MultiBandDiffusionEngine(synth.mbd_checkpoint(mbd_cfg, 0), mbd_cfg, device=device, max_seconds=6.0)
     frames = N_NEW // 2
     text_ids = torch.randint(1025, 1537, (11,), generator=torch.Generator().manual_seed(5)).tolist() + [1537]
 
     def pipeline_pass(seed):
+        t_a = time.perf_counter()
         toks = U.generate_batch(model, prompts, h_spk_pinned, max_new_tokens=N_NEW, end_of_audio_token=9999, seed=seed, **SAMPLING)
-        secs, t_s2, t_voc = 0.0, 0.0, 0.0
+        t_b = time.perf_counter()
+        secs, t_s2, t_voc, t_mbd, t_post, nbytes = 0.0, 0.0, 0.0, 0.0, 0.0, 0
         for u in range(utts):
             _, cb = flattened_interleaved_decode(toks[u].tolist())
             cb = [(c + [7] * frames)[:frames] for c in cb]   # random-init weights do not alternate codebooks: pad/cut to 375 frames
@@ -379,25 +386,38 @@ def pipeline_leg(model, prompts, spk, h_spk_pinned, utts, steps, device, world, 
                                 s2.forward_tokens(idx, spk[u:u + 1], 1.0, 200, seed=seed)[0, :, len(text_ids):len(text_ids) + frames]])
             codes8 = codes8.clamp_(0, 1023)
             torch.cuda.synchronize(device); t1 = time.perf_counter()
-            wav = codec.decode(codes8).cpu()
-            t2 = time.perf_counter()
-            secs += wav.numel() / 24000.0; t_s2 += t1 - t0; t_voc += t2 - t1
-        return secs, t_s2, t_voc
+            wav = codec.decode(codes8)
+            cond = codec.decode_latent(codes8)
+            torch.cuda.synchronize(device); t2 = time.perf_counter()
+            wav = mbd.tokens_to_wav(cond, wav, seed=seed)
+            torch.cuda.synchronize(device); t3 = time.perf_counter()
+            blob = A.wav_bytes_on_device(wav, 24000)          # loudness -14 LUFS + tanh compressor + PCM16 on device, bytes to host
+            t4 = time.perf_counter()
+            secs += wav.numel() / 24000.0; t_s2 += t1 - t0; t_voc += t2 - t1; t_mbd += t3 - t2; t_post += t4 - t3; nbytes += len(blob)
+        return secs, t_b - t_a, t_s2, t_voc, t_mbd, t_post
 
     pipeline_pass(1)
     barrier()
     t0 = time.perf_counter()
-    audio_s = s2_s = voc_s = 0.0
+    acc = [0.0] * 6
     for k in range(steps):
         r = pipeline_pass(5000 + k)
-        audio_s += r[0]; s2_s += r[1]; voc_s += r[2]
+        acc = [a + b for a, b in zip(acc, r)]
     barrier()
     pipe_s = time.perf_counter() - t0
-    return {"audio_sec_per_s": round(audio_s * world / pipe_s, 3), "audio_s_per_step": round(audio_s / steps, 3),
-            "ms_per_step": {"total": round(pipe_s / steps * 1e3, 2), "stage2": round(s2_s / steps * 1e3, 2),
-                            "encodec_decoder": round(voc_s / steps * 1e3, 2)},
-            "coverage": "stage-1 (750 tokens) + token adapters + stage-2 (6 codebooks) + EnCodec SEANet decoder, wav copied to host; "
-                        "the multi-band-diffusion refinement and DeepFilterNet of the reference are NOT implemented"}
+    audio_s, s1_s, s2_s, voc_s, mbd_s, post_s = acc
+    mbd.close(); codec.close(); s2.close()
+    u = mbd_cfg.unet
+    return {"audio_sec_per_s": round(audio_s * world / pipe_s, 3),
+            "audio_sec_per_s_without_mbd": round(audio_s * world / (pipe_s - mbd_s), 3),
+            "audio_s_per_step": round(audio_s / steps, 3),
+            "ms_per_step": {"total": round(pipe_s / steps * 1e3, 2), "stage1": round(s1_s / steps * 1e3, 2), "stage2": round(s2_s / steps * 1e3, 2),
+                            "encodec_decoder": round(voc_s / steps * 1e3, 2), "multiband_diffusion": round(mbd_s / steps * 1e3, 2),
+                            "audio_post_pcm16": round(post_s / steps * 1e3, 2)},
+            "mbd_config": f"PARAMETRISED, parity unpinned: {mbd_cfg.n_models} band UNets (hidden {u.hidden}, depth {u.depth}, growth {u.growth}, "
+                          f"k{u.kernel}/s{u.stride}, {u.res_blocks} res block) x {len(mbd_cfg.steps()) - 1} calls, {mbd_cfg.eq_bands}-band re-EQ, fp32 CUDA-core convolutions",
+            "coverage": "stage-1 (750 tokens) + token adapters + stage-2 (6 codebooks) + EnCodec SEANet decoder + multi-band diffusion "
+                        "+ loudness/compressor/PCM16 on device, wav bytes on the host; DeepFilterNet is NOT implemented"}
 
 
 def _oracle_stage1(dtype):

@@ -234,6 +234,43 @@ int mvb_voc_decode_latent(mvb_voc* h, const int32_t* d_codes, int32_t T, float* 
 int mvb_voc_decode(mvb_voc* h, const int32_t* d_codes, int32_t T, float* d_wav, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Multi-band-diffusion vocoder (second half) == `mbd.tokens_to_wav` (fam/llm/decoders.py:84-85 ->
+ * audiocraft 1.2.0 MultiBandDiffusion.tokens_to_wav) after the codec decode: n_models band UNets x n_calls sampler steps
+ * conditioned on the codec latent, per-band output processors, sum, 32-band re-EQ against the EnCodec waveform.
+ * PARITY UNPINNED (audiocraft / julius / mbd_comp_8.pt are not available): the configuration is a parameter. */
+typedef struct mvb_mbd_config {
+  int32_t n_models;        /* band models summed by MultiBandDiffusion.generate (4) */
+  int32_t chin, hidden, depth, res_blocks, norm_groups, kernel, stride;   /* DiffusionUnet kwargs; (kernel, stride) in {(8,4), (4,2)} */
+  float   growth;
+  int32_t emb_all_layers;  /* step embedding added after every encoder level (else only the first) */
+  int32_t codec_dim;       /* 128: channels of the condition (codec latent) */
+  int32_t num_steps;       /* rows of the step-embedding tables (1000) */
+  int32_t n_calls;         /* UNet evaluations per band model (20 for step_list = range(1000)[::-50] + [0]) */
+  float   noise_scale, clip;
+  int32_t proc_bands, proc_taps;   /* MultiBandProcessor: SplitBands(n_bands) and its filter length */
+  int32_t eq_bands, eq_taps;       /* re_eq: 32 bands and the filter length */
+  int32_t max_samples;     /* workspace capacity (samples at 24 kHz) */
+} mvb_mbd_config;
+typedef struct mvb_mbd mvb_mbd;
+/* fp32 arena tensors (offsets, host): for every band model, in this order
+ *   per encoder level: conv.weight [C, Cin, k], norm.weight, norm.bias, res_blocks x {norm1.w, norm1.b, conv1.w [C,C,3], conv1.b,
+ *                      norm2.w, norm2.b, conv2.w, conv2.b}, step-embedding table [num_steps, C]
+ *   conv_codec.weight [C_bottleneck, codec_dim, 1], conv_codec.bias
+ *   per decoder level (deepest first): res_blocks x {8 tensors}, norm.weight, norm.bias, convtr.weight [C, C_out, k]
+ *   processor scale [proc_bands] = (std / target_std) ** power_std, processor mean [proc_bands]
+ * then three globals: processor low-pass bank [proc_bands - 1, proc_taps], re-EQ bank [eq_bands - 1, eq_taps],
+ * schedule table [n_calls, 4] = {a, b, sigma, step}:  previous = clamp((current - a * estimate) * b + sigma * noise). */
+size_t mvb_mbd_workspace_bytes(const mvb_mbd_config* cfg);
+int mvb_mbd_create(const mvb_mbd_config* cfg, const void* d_arena, size_t arena_bytes, const uint64_t* offsets, void* d_workspace,
+                   mvb_mbd** out);
+int mvb_mbd_destroy(mvb_mbd* h);
+/* d_cond fp32 [codec_dim, n_frames] (mvb_voc_decode_latent), d_wav_encodec fp32 [n_samples] (mvb_voc_decode),
+ * d_noise fp32 [n_models, n_calls, n_samples] standard-normal draws (row 0 = initial sample, row i = the draw added after
+ * call i - 1 ... see oracle/mbd_port.py) or NULL for on-device Philox (seed); d_wav_out fp32 [n_samples]. */
+int mvb_mbd_tokens_to_wav(mvb_mbd* h, const float* d_cond, int32_t n_frames, const float* d_wav_encodec, int32_t n_samples,
+                          const float* d_noise, uint64_t seed, float* d_wav_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Speaker encoder: fam/quantiser/audio/speaker_encoder/{audio.py:10-22, model.py:50-103}.
  * 16 kHz mono fp32 waveform -> power mel spectrogram (n_fft 400, hop 160, 40 Slaney bands, centered, zero padded) ->
  * 3-layer LSTM(40 -> 256) over partial windows of 160 frames -> linear -> ReLU -> L2 norm -> mean -> L2 norm. */

@@ -103,6 +103,7 @@ struct PcParams {
   int fused;       // 1: sample in the kernel and advance the decode state (top_k == 0 only); 0: leave normalised logits
   int pf_mode;     // 0: no L2 prefetch, 1: by the producer while the ring is full, 2: dedicated prefetch warp
   int pf_ahead;    // weight tiles prefetched into L2 ahead of the smem ring
+  int kv_pf;       // 1: L2-prefetch the next layer's KV tiles while this layer's projections stream
   int epi_mode;    // WB epilogue: 0 = 32x32b loads + red.v4, 1 = 32x32b loads + scalar red, 2 = 16x256b fragment loads + scalar red
   float eps;
   PcMat m_qkv, m_o, m_w13, m_w2, m_head;
@@ -301,6 +302,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   constexpr int RH = Cfg::RH;
   constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
   constexpr int TILE_ROWS = Cfg::TILE_ROWS;
+  constexpr int SG = 2;   // activation chunks staged per thread per trip (3-4 were measured: the arrays spill, staging gets slower)
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by POINTER ARITHMETIC on the shared array: an integer round trip would lose the .shared state
   // space and turn every access below into a generic LD/ST (higher latency, no LDS/STS)
@@ -459,6 +461,23 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           __syncwarp();
         }
       };
+      // Pull every KV tile this CTA will need for layer l into L2 ahead of time: with only PC_NKV tile slots in shared
+      // memory the attention phase would otherwise pay an HBM round trip per tile (batch 8: 55 MB of K/V per layer).
+      auto kv_prefetch_l2 = [&](int l) {
+        const char* kbase = p.kv + (size_t)l * 2 * p.kv_half;
+        const char* vbase = kbase + p.kv_half;
+        const int n_tiles = sh.n_att_tiles;
+        for (int i = 0; i < n_tiles; ++i) {
+          const AttTile e = sh.att_tab[i];
+          const uint32_t bytes = (e.meta & 0xffu) * 128u * (uint32_t)esz;
+          if (bytes == 0) continue;
+          if (ptx::elect_one()) {
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kbase + e.off), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(vbase + e.off), "r"(bytes) : "memory");
+          }
+          __syncwarp();
+        }
+      };
       for (int step = 0; step < p.n_steps; ++step) {
         for (int l = 0; l < p.n_layer; ++l) {
           if (l == 0) {
@@ -468,6 +487,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           } else {
             kv_units(l, PC_NKV, 1 << 30);                       // (units beyond the prefetched ones)
           }
+          if (p.kv_pf && l + 1 < p.n_layer) kv_prefetch_l2(l + 1);
           gemm_tiles(&tm_o, &tm_o, 1 << 30, s_o, l);
           gemm_tiles(&tm_w1, &tm_w3, T1, s_w13, l);
           gemm_tiles(&tm_w2, &tm_w2, 1 << 30, s_w2, l);
@@ -584,13 +604,13 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       if (sl.nt == 0) return;
       const int nchunk = (sl.kb1 - sl.kb0) * 8;
       const int total = p.R * nchunk;
-      // 2 chunks (6 loads) in flight per thread per trip; the trip count is warp-uniform (the statistic uses warp votes)
-      for (int base = cw * 32; base < total; base += 2 * 128) {
+      // SG chunks (3 SG loads) in flight per thread per trip; the trip count is warp-uniform (the statistic uses warp votes)
+      for (int base = cw * 32; base < total; base += SG * 128) {
         const int i0 = base + lane;
-        float4 la[2], lb[2];
-        uint4 lg[2];
+        float4 la[SG], lb[SG];
+        uint4 lg[SG];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < SG; ++j) {
           const int i = i0 + j * 128;
           if (i < total) {
             const int n = i / nchunk, c = i - n * nchunk;
@@ -620,7 +640,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           }
         }
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < SG; ++j) {
           const int i = i0 + j * 128;
           const bool act = i < total;                  // (trip counts are warp-uniform except in the last warp-trip)
           int n = 0, c = 0;
@@ -935,7 +955,8 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
               ptx::mbar_wait(ptx::smem_u32(sh.kv_full + ks), ph);
               const uint8_t* kt = kvbuf + (size_t)ks * 2 * PC_KV_TILE_BYTES;
               const uint8_t* vt = kt + PC_KV_TILE_BYTES;
-              // each half-warp owns positions hw, hw+8, ...; two positions per trip for ILP
+              // each half-warp owns positions hw, hw+8, ...; two positions per trip for ILP (four per trip was measured:
+              // the extra 32 live registers spill in this 255-register kernel and the phase gets 15-30 % slower)
               for (int pb = hw; pb < npos; pb += 16) {
                 const int pA = pb, pB = pb + 8;
                 const bool vB = pB < npos;
@@ -1082,11 +1103,11 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         if (s_w2.nt > 0) {
           const int nchunk = (s_w2.kb1 - s_w2.kb0) * 8;
           const int total = p.R * nchunk;
-          for (int i0 = ct; i0 < total; i0 += 2 * 128) {
-            float4 g0[2], g1[2], u0[2], u1[2];
-            float ssn[2];
+          for (int i0 = ct; i0 < total; i0 += SG * 128) {
+            float4 g0[SG], g1[SG], u0[SG], u1[SG];
+            float ssn[SG];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < SG; ++j) {
               const int i = i0 + j * 128;
               if (i < total) {
                 const int n = i / nchunk, c = i - n * nchunk;
@@ -1098,7 +1119,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
               }
             }
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
+            for (int j = 0; j < SG; ++j) {
               const int i = i0 + j * 128;
               if (i < total) {
                 const int n = i / nchunk, c = i - n * nchunk;
@@ -1161,15 +1182,15 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           const float g = sp.guidance, omg = __fsub_rn(1.0f, sp.guidance);
           const float tdiv = fmaxf(sp.temperature, 1e-5f);
           float mx = -INFINITY;
-          for (int v0 = ct; v0 < V; v0 += 24 * 128) {       // up to 48 loads in flight per thread: one L2 round trip for V <= 3072
-            float la[24], lb[24];
+          for (int v0 = ct; v0 < V; v0 += 12 * 128) {       // 24 loads in flight per thread per trip
+            float la[12], lb[12];
 #pragma unroll
-            for (int i = 0; i < 24; ++i) {
+            for (int i = 0; i < 12; ++i) {
               const int v = v0 + i * 128;
               if (v < V) { la[i] = __ldcg(lc + v); lb[i] = __ldcg(lu + v); }
             }
 #pragma unroll
-            for (int i = 0; i < 24; ++i) {
+            for (int i = 0; i < 12; ++i) {
               const int v = v0 + i * 128;
               if (v < V) {
                 const float k = __fdiv_rn(__fadd_rn(__fmul_rn(g, la[i] * rs_c), __fmul_rn(omg, lb[i] * rs_u)), tdiv);

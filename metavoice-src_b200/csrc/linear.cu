@@ -34,19 +34,38 @@ extern "C" int mvb_linear(const void* d_W, int32_t M, int32_t K, const float* d_
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   GemmPlan g = plan_gemm(M, K, NB, false, n_sm);
   if (ksplit_override > 0) {
-    g.ksplit = ksplit_override;
+    // every split of a tile waits for its siblings inside the kernel: all tiles x ksplit CTAs must be co-resident
+    const int cap = n_sm / g.tiles > 0 ? n_sm / g.tiles : 1;
+    g.ksplit = ksplit_override < cap ? ksplit_override : cap;
+    if (g.tiles > 128) g.ksplit = 1;
     g.scratch_floats = (size_t)g.tiles * g.ksplit * NB * 128;
   }
+  // Scratch buffers are cached per device and only ever grow (no allocation on the steady-state path; this standalone
+  // operator has no caller-provided workspace, unlike the engine handles).
+  struct Cache { void* p = nullptr; size_t cap = 0; };
+  static Cache cB[16], cS[16], cT[16];
+  auto ensure = [&](Cache& c, size_t bytes) -> cudaError_t {
+    if (c.cap >= bytes) return cudaSuccess;
+    if (c.p) cudaFree(c.p);
+    c.p = nullptr; c.cap = 0;
+    cudaError_t e = cudaMalloc(&c.p, bytes);
+    if (e == cudaSuccess) c.cap = bytes;
+    return e;
+  };
+  if (dev < 0 || dev >= 16) return mvb::set_error(MVB_ERR_UNSUPPORTED, "mvb_linear: device index %d", dev);
   __nv_bfloat16* B = nullptr;
   float* scratch = nullptr;
   unsigned* tickets = nullptr;
   CUtensorMap tA, tB;
   GemmP p{};
-  LCK(cudaMalloc(&B, (size_t)NB * K * 2));
+  LCK(ensure(cB[dev], (size_t)NB * K * 2));
+  LCK(ensure(cS[dev], sizeof(float) * (g.scratch_floats ? g.scratch_floats : 1)));
+  LCK(ensure(cT[dev], sizeof(unsigned) * 256));
+  B = reinterpret_cast<__nv_bfloat16*>(cB[dev].p);
+  scratch = reinterpret_cast<float*>(cS[dev].p);
+  tickets = reinterpret_cast<unsigned*>(cT[dev].p);
   LCK(cudaMemsetAsync(B, 0, (size_t)NB * K * 2, s));
-  LCK(cudaMalloc(&scratch, sizeof(float) * (g.scratch_floats ? g.scratch_floats : 1)));
-  LCK(cudaMalloc(&tickets, sizeof(unsigned) * g.tiles));
-  LCK(cudaMemsetAsync(tickets, 0, sizeof(unsigned) * g.tiles, s));
+  LCK(cudaMemsetAsync(tickets, 0, sizeof(unsigned) * 256, s));
   if (!make_tmap_bf16(&tA, d_W, (uint64_t)M, (uint64_t)K, 128) || !make_tmap_bf16(&tB, B, (uint64_t)NB, (uint64_t)K, (uint32_t)NB)) {
     rc = mvb::set_error(MVB_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     goto done;
@@ -61,8 +80,5 @@ extern "C" int mvb_linear(const void* d_W, int32_t M, int32_t K, const float* d_
     LCK(launch_umma_gemm<G_STORE>(s, tA, tA, tB, p, g));
   LCK(cudaStreamSynchronize(s));
 done:
-  if (B) cudaFree(B);
-  if (scratch) cudaFree(scratch);
-  if (tickets) cudaFree(tickets);
   return rc;
 }

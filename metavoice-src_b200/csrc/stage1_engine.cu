@@ -158,9 +158,9 @@ struct mvb_s1 {
   bool pc_ok = false;
   bool trace = false;
   // persistent-kernel switches, read once at create (MVB_PC_WB, MVB_PC_FUSED, MVB_PF_MODE, MVB_PF_AHEAD)
-  bool wb = true;                                     // streamed weights as the N = 256 UMMA B operand
+  bool wb = false;                                    // streamed weights as the N = 256 UMMA B operand (measured slower: off)
   bool fused = true;                                  // sample inside the persistent kernel (multi-token launches)
-  int pf_mode = 1, pf_ahead = 8, epi_mode = 2;
+  int pf_mode = 1, pf_ahead = 8, epi_mode = 2, kv_pf = 0;
   CUtensorMap tm3[2][6];                              // [WB] 3-D (k, row, layer) maps: wqkv, wo, w1, w3, w2, head
   PcMat pm[2][5];
   bool pc_ok2[2] = {false, false};
@@ -306,6 +306,7 @@ extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size
   if (const char* e = getenv("MVB_PF_AHEAD")) h->pf_ahead = atoi(e);
   if (const char* e = getenv("MVB_PF_MODE")) h->pf_mode = atoi(e);
   if (const char* e = getenv("MVB_PC_EPI")) h->epi_mode = atoi(e);
+  if (const char* e = getenv("MVB_PC_KVPF")) h->kv_pf = atoi(e);
   if (const char* e = getenv("MVB_PC_WB")) h->wb = atoi(e) != 0;
   if (const char* e = getenv("MVB_PC_FUSED")) h->fused = atoi(e) != 0;
   h->h_topk.assign(cfg->max_utts, 0);
@@ -554,7 +555,7 @@ static int launch_persistent(mvb_s1* h, cudaStream_t s, int n_utts, int n_steps,
   PcParams p{};
   p.n_layer = c.n_layer; p.D = c.dim; p.F = c.intermediate; p.V = c.vocab; p.H = c.n_head; p.S_max = c.block_size;
   p.n_steps = n_steps; p.fused = fused ? 1 : 0;
-  p.pf_mode = h->pf_mode; p.pf_ahead = h->pf_ahead; p.epi_mode = h->epi_mode;
+  p.pf_mode = h->pf_mode; p.pf_ahead = h->pf_ahead; p.epi_mode = h->epi_mode; p.kv_pf = h->kv_pf;
   p.R = 2 * n_utts; p.n_utts = n_utts; p.kv_fp32 = c.kv_dtype == MVB_KV_FP32; p.eps = c.norm_eps;
   p.m_qkv = h->pm[wbv][0]; p.m_o = h->pm[wbv][1]; p.m_w13 = h->pm[wbv][2]; p.m_w2 = h->pm[wbv][3]; p.m_head = h->pm[wbv][4];
   p.attn_norm = h->lw(0, 0); p.ffn_norm = h->lw(0, 3); p.out_norm = h->w(3);

@@ -7,6 +7,7 @@
 // the reference); sampling is one CTA per (hierarchy, position).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -52,70 +53,94 @@ __global__ void __launch_bounds__(256) k_s2_spk(const __nv_bfloat16* __restrict_
   if (lane == 0) out[(size_t)b * E + warp] = acc;
 }
 
-// Bidirectional attention (attn.py:148-155 with is_causal=False): one query per thread, K/V tiles of 32 keys in smem.
+// Bidirectional attention (attn.py:148-155 with is_causal=False).  A CTA owns 32 queries of one head; every query is
+// carried by a group of 4 lanes (each lane keeps HS/4 dimensions of q and of the output, scores are completed with two
+// shuffles), K/V tiles of 64 keys are staged in shared memory (64 / 32 keys per tile) with 128-bit loads and broadcast to the 8 queries of a warp.
 template <int HS>
 __global__ void __launch_bounds__(128) k_s2_attn(const float* __restrict__ qkv, float* __restrict__ out, int t, int E, int n_head) {
-  __shared__ float sk[32][HS];
-  __shared__ float sv[32][HS];
+  constexpr int DL = HS / 4;            // dimensions per lane
+  constexpr int KT = HS == 64 ? 64 : 32;   // keys per tile (32 KB of static shared memory either way)
+  __shared__ __align__(16) float sk[KT][HS];
+  __shared__ __align__(16) float sv[KT][HS];
   const int h = blockIdx.y, b = blockIdx.z;
-  const int qi = blockIdx.x * 128 + threadIdx.x;
+  const int tid = threadIdx.x, part = tid & 3;
+  const int qi = blockIdx.x * 32 + (tid >> 2);
   const bool active = qi < t;
   const float scale = rsqrtf((float)HS);
-  float q[HS], o[HS];
-  const float* qp = qkv + ((size_t)b * t + (active ? qi : 0)) * 3 * E + h * HS;
+  float q[DL], o[DL];
+  const float* qp = qkv + ((size_t)b * t + (active ? qi : 0)) * 3 * E + h * HS + part * DL;
 #pragma unroll
-  for (int d = 0; d < HS; ++d) {
-    q[d] = qp[d] * scale;
-    o[d] = 0.f;
+  for (int d = 0; d < DL; d += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(qp + d);
+    q[d] = v.x * scale; q[d + 1] = v.y * scale; q[d + 2] = v.z * scale; q[d + 3] = v.w * scale;
+    o[d] = o[d + 1] = o[d + 2] = o[d + 3] = 0.f;
   }
   float m = -INFINITY, l = 0.f;
-  for (int k0 = 0; k0 < t; k0 += 32) {
+  for (int k0 = 0; k0 < t; k0 += KT) {
     __syncthreads();
-    for (int i = threadIdx.x; i < 32 * HS; i += 128) {
-      const int kk = i / HS, d = i - kk * HS;
+    for (int i = tid; i < KT * HS / 4; i += 128) {
+      const int kk = i / (HS / 4), d4 = i - kk * (HS / 4);
       const bool ok = k0 + kk < t;
-      const float* kp = qkv + ((size_t)b * t + (ok ? k0 + kk : 0)) * 3 * E + E + h * HS + d;
-      sk[kk][d] = ok ? kp[0] : 0.f;
-      sv[kk][d] = ok ? kp[E] : 0.f;
+      const float* kp = qkv + ((size_t)b * t + (ok ? k0 + kk : 0)) * 3 * E + E + h * HS + d4 * 4;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4*>(&sk[kk][0])[d4] = ok ? *reinterpret_cast<const float4*>(kp) : z;
+      reinterpret_cast<float4*>(&sv[kk][0])[d4] = ok ? *reinterpret_cast<const float4*>(kp + E) : z;
     }
     __syncthreads();
-    const int nk = min(32, t - k0);
-    float s[32];
-    float mx = m;
+    const int nk = min(KT, t - k0);
+    for (int kk = 0; kk < nk; kk += 4) {           // 4 keys per trip: independent score chains
+      float sc[4];
 #pragma unroll
-    for (int kk = 0; kk < 32; ++kk) {
-      float a = 0.f;
+      for (int j = 0; j < 4; ++j) {
+        float a = 0.f;
+        const float* kr = &sk[kk + j][part * DL];
 #pragma unroll
-      for (int d = 0; d < HS; ++d) a = fmaf(q[d], sk[kk][d], a);
-      s[kk] = kk < nk ? a : -INFINITY;
-      mx = fmaxf(mx, s[kk]);
+        for (int d = 0; d < DL; ++d) a = fmaf(q[d], kr[d], a);
+        sc[j] = a;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], 1);
+        sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], 2);
+        if (kk + j >= nk) sc[j] = -INFINITY;
+      }
+      const float mx = fmaxf(fmaxf(m, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));
+      const float corr = __expf(m - mx);
+      float pw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pw[j] = __expf(sc[j] - mx);
+      l = l * corr + (pw[0] + pw[1]) + (pw[2] + pw[3]);
+#pragma unroll
+      for (int d = 0; d < DL; ++d) {
+        float acc = o[d] * corr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc = fmaf(pw[j], sv[kk + j][part * DL + d], acc);
+        o[d] = acc;
+      }
+      m = mx;
     }
-    const float corr = __expf(m - mx);
-    l *= corr;
-#pragma unroll
-    for (int d = 0; d < HS; ++d) o[d] *= corr;
-#pragma unroll
-    for (int kk = 0; kk < 32; ++kk) {
-      const float pw = __expf(s[kk] - mx);
-      l += pw;
-#pragma unroll
-      for (int d = 0; d < HS; ++d) o[d] = fmaf(pw, sv[kk][d], o[d]);
-    }
-    m = mx;
   }
   if (active) {
-    float* op = out + ((size_t)b * t + qi) * E + h * HS;
+    float* op = out + ((size_t)b * t + qi) * E + h * HS + part * DL;
     const float inv = 1.f / l;
 #pragma unroll
-    for (int d = 0; d < HS; ++d) op[d] = o[d] * inv;
+    for (int d = 0; d < DL; d += 4)
+      *reinterpret_cast<float4*>(op + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
   }
 }
 
 // _non_causal_sample for one (hierarchy, row): logits / T, top-k threshold, softmax, argmax(p / Exp(1)).
 constexpr int S2_PAD = 2048;
-__global__ void __launch_bounds__(256) k_s2_sample(const float* __restrict__ logits, int V, float temperature, int top_k,
-                                                   const float* __restrict__ noise, unsigned long long seed, int* __restrict__ out,
-                                                   int n_rows) {
+struct S2SampleParams {   // lives in device memory so that a captured graph can be replayed with new values
+  float temperature;
+  int top_k;
+  unsigned long long seed;
+};
+__global__ void __launch_bounds__(256) k_s2_sample(const float* __restrict__ logits, int V, const S2SampleParams* __restrict__ prm,
+                                                   const float* __restrict__ noise, int* __restrict__ out, int n_rows) {
+  const float temperature = prm->temperature;
+  const int top_k = prm->top_k;
+  const unsigned long long seed = prm->seed;
   __shared__ float key[S2_PAD];
   __shared__ float red[8];
   __shared__ unsigned long long rbest[8];
@@ -207,6 +232,13 @@ struct mvb_s2 {
   __nv_bfloat16* B;
   unsigned* tickets;
   int* tokens;
+  int* idx_stage;          // [max_batch, n_in, t] inputs copied here so that the captured graph only touches internal buffers
+  float* spk_stage;        // [max_batch, spk_dim]
+  S2SampleParams* params;  // device copy of the sampling parameters
+  S2SampleParams* h_params = nullptr;   // pinned
+  bool use_graph = true;
+  cudaStream_t cap_stream = nullptr;
+  cudaGraphExec_t graphs[2][65] = {};   // [has speaker][batch]
   const __nv_bfloat16** wte_dev;
   std::vector<CUtensorMap> tmW;   // per layer {c_attn, c_proj, w1, w3, mlp.c_proj}, then heads
   CUtensorMap tmB_E, tmB_H;
@@ -224,7 +256,8 @@ static size_t s2_align(size_t v) { return (v + 255) / 256 * 256; }
 static int s2_hidden(const mvb_s2_config* c) { return c->hidden; }
 
 static size_t s2_layout(const mvb_s2_config* c, size_t* o_x, size_t* o_qkv, size_t* o_att, size_t* o_ffn, size_t* o_logits, size_t* o_spk,
-                        size_t* o_B, size_t* o_scratch, size_t* o_tickets, size_t* o_tokens, size_t* o_wte) {
+                        size_t* o_B, size_t* o_scratch, size_t* o_tickets, size_t* o_tokens, size_t* o_wte, size_t* o_idx = nullptr,
+                        size_t* o_spkst = nullptr, size_t* o_prm = nullptr) {
   const size_t rows = (size_t)c->max_batch * c->block_size, E = c->n_embd, Hd = s2_hidden(c);
   size_t vmax = 0;
   for (int i = 0; i < c->n_out; ++i) vmax = vmax > (size_t)c->vocab_out[i] ? vmax : (size_t)c->vocab_out[i];
@@ -247,6 +280,10 @@ static size_t s2_layout(const mvb_s2_config* c, size_t* o_x, size_t* o_qkv, size
   *o_tickets = take(256 * 4);
   *o_tokens = take((size_t)c->n_out * rows * 4);
   *o_wte = take(16 * sizeof(void*));
+  const size_t a = take((size_t)c->max_batch * c->n_in * c->block_size * 4), b2 = take((size_t)c->max_batch * c->spk_dim * 4), p3 = take(256);
+  if (o_idx) *o_idx = a;
+  if (o_spkst) *o_spkst = b2;
+  if (o_prm) *o_prm = p3;
   return o;
 }
 
@@ -258,7 +295,7 @@ static int s2_validate(const mvb_s2_config* c) {
   if (c->n_in < 1 || c->n_in > 8 || c->n_out < 1 || c->n_out > 8) return mvb::set_error(MVB_ERR_ARG, "hierarchy counts out of range");
   for (int i = 0; i < c->n_out; ++i)
     if (c->vocab_out[i] > S2_PAD) return mvb::set_error(MVB_ERR_UNSUPPORTED, "target vocab > %d", S2_PAD);
-  if (c->max_batch < 1 || c->block_size < 1) return mvb::set_error(MVB_ERR_ARG, "bad batch / block size");
+  if (c->max_batch < 1 || c->max_batch > 64 || c->block_size < 1) return mvb::set_error(MVB_ERR_ARG, "bad batch / block size");
   return MVB_OK;
 }
 
@@ -284,8 +321,10 @@ extern "C" int mvb_s2_create(const mvb_s2_config* cfg, const void* d_arena, size
   for (uint64_t o : h->off)
     if (o % 16 || o >= arena_bytes) { delete h; return mvb::set_error(MVB_ERR_ARG, "bad weight offset"); }
   h->ws = reinterpret_cast<char*>(d_ws);
-  size_t ox, oq, oa, of, ol, os, oB, osc, ot, otok, ow;
-  s2_layout(cfg, &ox, &oq, &oa, &of, &ol, &os, &oB, &osc, &ot, &otok, &ow);
+  size_t ox, oq, oa, of, ol, os, oB, osc, ot, otok, ow, oidx, ospk, oprm;
+  s2_layout(cfg, &ox, &oq, &oa, &of, &ol, &os, &oB, &osc, &ot, &otok, &ow, &oidx, &ospk, &oprm);
+  h->idx_stage = (int*)(h->ws + oidx); h->spk_stage = (float*)(h->ws + ospk); h->params = (S2SampleParams*)(h->ws + oprm);
+  h->use_graph = getenv("MVB_S2_NO_GRAPH") == nullptr;
   h->x = (float*)(h->ws + ox); h->qkv = (float*)(h->ws + oq); h->att = (float*)(h->ws + oa); h->ffn = (float*)(h->ws + of);
   h->logits = (float*)(h->ws + ol); h->spk_proj = (float*)(h->ws + os); h->B = (__nv_bfloat16*)(h->ws + oB);
   h->scratch = (float*)(h->ws + osc); h->tickets = (unsigned*)(h->ws + ot); h->tokens = (int*)(h->ws + otok);
@@ -308,11 +347,22 @@ extern "C" int mvb_s2_create(const mvb_s2_config* cfg, const void* d_arena, size
   ok = ok && make_tmap_bf16(&h->tmB_E, h->B, 2 * S2_ROWS, E, 2 * S2_ROWS);
   ok = ok && make_tmap_bf16(&h->tmB_H, h->B, 2 * S2_ROWS, Hd, 2 * S2_ROWS);
   if (!ok) { delete h; return mvb::set_error(MVB_ERR_CUDA, "cuTensorMapEncodeTiled failed (stage 2)"); }
+  if (cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost(&h->h_params, sizeof(S2SampleParams)) != cudaSuccess) {
+    delete h;
+    return mvb::set_error(MVB_ERR_CUDA, "stage 2: stream / pinned buffer allocation failed");
+  }
   *out = h;
   return MVB_OK;
 }
 
 extern "C" int mvb_s2_destroy(mvb_s2* h) {
+  if (!h) return MVB_OK;
+  for (auto& row : h->graphs)
+    for (auto& g : row)
+      if (g) cudaGraphExecDestroy(g);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h->h_params) cudaFreeHost(h->h_params);
   delete h;
   return MVB_OK;
 }
@@ -335,25 +385,21 @@ static int s2_linear(mvb_s2* h, cudaStream_t s, int rows, const float* x, int ld
   return MVB_OK;
 }
 
-extern "C" int mvb_s2_forward(mvb_s2* h, int32_t batch, const int32_t* d_idx, const float* d_spk, float temperature, int32_t top_k,
-                              const float* d_noise, uint64_t seed, int32_t* d_tokens, float* d_logits_out, void* stream) {
-  if (!h || !d_idx || !d_tokens) return mvb::set_error(MVB_ERR_ARG, "null argument");
+// embed -> n_layer x {attention, MLP} -> ln_f + heads -> sampler, on internal buffers only (graph-capturable)
+static int s2_body(mvb_s2* h, cudaStream_t s, int batch, bool has_spk, const float* d_noise) {
   const mvb_s2_config& c = h->cfg;
-  if (batch < 1 || batch > c.max_batch) return mvb::set_error(MVB_ERR_ARG, "batch %d out of range", batch);
-  if (!(temperature > 0.f)) return mvb::set_error(MVB_ERR_ARG, "temperature must be positive");
-  cudaStream_t s = (cudaStream_t)stream;
   const int t = c.block_size, rows = batch * t, E = c.n_embd, Hd = h->hidden;
   SCK(cudaMemsetAsync(h->tickets, 0, 256 * 4, s));
-  if (d_spk) {
-    k_s2_spk<<<dim3((E * 32 + 255) / 256, batch), 256, 0, s>>>(h->w(h->g_spk()), d_spk, h->spk_proj, E, c.spk_dim);
+  if (has_spk) {
+    k_s2_spk<<<dim3((E * 32 + 255) / 256, batch), 256, 0, s>>>(h->w(h->g_spk()), h->spk_stage, h->spk_proj, E, c.spk_dim);
     SCK(cudaGetLastError());
   }
-  k_s2_embed<<<rows, 128, 0, s>>>(d_idx, c.n_in, t, h->wte_dev, h->w(h->g_wpe()), d_spk ? h->spk_proj : nullptr, h->x, E);
+  k_s2_embed<<<rows, 128, 0, s>>>(h->idx_stage, c.n_in, t, h->wte_dev, h->w(h->g_wpe()), has_spk ? h->spk_proj : nullptr, h->x, E);
   SCK(cudaGetLastError());
   const int hs = E / c.n_head;
   for (int l = 0; l < c.n_layer; ++l) {
     if (int e = s2_linear<G_STORE>(h, s, rows, h->x, E, h->w(h->g_layer(l, 0)), l * 5 + 0, l * 5 + 0, 3 * E, E, h->qkv, 3 * E)) return e;
-    dim3 ag((t + 127) / 128, c.n_head, batch);
+    dim3 ag((t + 31) / 32, c.n_head, batch);
     if (hs == 64) k_s2_attn<64><<<ag, 128, 0, s>>>(h->qkv, h->att, t, E, c.n_head);
     else k_s2_attn<128><<<ag, 128, 0, s>>>(h->qkv, h->att, t, E, c.n_head);
     SCK(cudaGetLastError());
@@ -361,16 +407,50 @@ extern "C" int mvb_s2_forward(mvb_s2* h, int32_t batch, const int32_t* d_idx, co
     if (int e = s2_linear<G_SWIGLU>(h, s, rows, h->x, E, h->w(h->g_layer(l, 3)), l * 5 + 2, l * 5 + 3, Hd, E, h->ffn, Hd)) return e;
     if (int e = s2_linear<G_RESID>(h, s, rows, h->ffn, Hd, nullptr, l * 5 + 4, l * 5 + 4, E, Hd, h->x, E)) return e;
   }
-  size_t vmax = 0;
-  for (int i = 0; i < c.n_out; ++i) vmax = vmax > (size_t)c.vocab_out[i] ? vmax : (size_t)c.vocab_out[i];
+  const int vmax = c.vocab_out[0];
   for (int i = 0; i < c.n_out; ++i) {
-    if (c.vocab_out[i] != (int)vmax) return mvb::set_error(MVB_ERR_UNSUPPORTED, "target vocabularies must be equal");
     const int hw = c.n_layer * 5 + i;
-    if (int e = s2_linear<G_STORE>(h, s, rows, h->x, E, h->w(h->g_lnf()), hw, hw, (int)vmax, E, h->logits + (size_t)i * rows * vmax, (int)vmax))
-      return e;
+    if (int e = s2_linear<G_STORE>(h, s, rows, h->x, E, h->w(h->g_lnf()), hw, hw, vmax, E, h->logits + (size_t)i * rows * vmax, vmax)) return e;
   }
-  k_s2_sample<<<dim3(rows, c.n_out), 256, 0, s>>>(h->logits, (int)vmax, temperature, top_k, d_noise, seed, h->tokens, rows);
+  k_s2_sample<<<dim3(rows, c.n_out), 256, 0, s>>>(h->logits, vmax, h->params, d_noise, h->tokens, rows);
   SCK(cudaGetLastError());
+  return MVB_OK;
+}
+
+extern "C" int mvb_s2_forward(mvb_s2* h, int32_t batch, const int32_t* d_idx, const float* d_spk, float temperature, int32_t top_k,
+                              const float* d_noise, uint64_t seed, int32_t* d_tokens, float* d_logits_out, void* stream) {
+  if (!h || !d_idx || !d_tokens) return mvb::set_error(MVB_ERR_ARG, "null argument");
+  const mvb_s2_config& c = h->cfg;
+  if (batch < 1 || batch > c.max_batch) return mvb::set_error(MVB_ERR_ARG, "batch %d out of range", batch);
+  if (!(temperature > 0.f)) return mvb::set_error(MVB_ERR_ARG, "temperature must be positive");
+  for (int i = 1; i < c.n_out; ++i)
+    if (c.vocab_out[i] != c.vocab_out[0]) return mvb::set_error(MVB_ERR_UNSUPPORTED, "target vocabularies must be equal");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int t = c.block_size, rows = batch * t;
+  const size_t vmax = c.vocab_out[0];
+  // inputs -> internal staging buffers: the forward pass itself (~500 small launches: 8 passes of 128 rows per Linear)
+  // only touches library memory and is replayed as ONE CUDA graph per (batch, speaker) signature
+  SCK(cudaMemcpyAsync(h->idx_stage, d_idx, sizeof(int) * (size_t)batch * c.n_in * t, cudaMemcpyDeviceToDevice, s));
+  if (d_spk) SCK(cudaMemcpyAsync(h->spk_stage, d_spk, sizeof(float) * (size_t)batch * c.spk_dim, cudaMemcpyDeviceToDevice, s));
+  SCK(cudaStreamSynchronize(s));            // h_params is reused across calls: the previous upload must have been consumed
+  h->h_params->temperature = temperature; h->h_params->top_k = top_k; h->h_params->seed = seed;
+  SCK(cudaMemcpyAsync(h->params, h->h_params, sizeof(S2SampleParams), cudaMemcpyHostToDevice, s));
+  if (h->use_graph && d_noise == nullptr) {
+    cudaGraphExec_t& ge = h->graphs[d_spk ? 1 : 0][batch];
+    if (!ge) {
+      cudaGraph_t g;
+      SCK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+      const int e = s2_body(h, h->cap_stream, batch, d_spk != nullptr, nullptr);
+      const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &g);
+      if (e) return e;
+      SCK(ce);
+      SCK(cudaGraphInstantiate(&ge, g, 0));
+      SCK(cudaGraphDestroy(g));
+    }
+    SCK(cudaGraphLaunch(ge, s));
+  } else {
+    if (int e = s2_body(h, s, batch, d_spk != nullptr, d_noise)) return e;
+  }
   // tokens [n_out, batch*t] -> caller layout [batch, n_out, t]
   for (int b = 0; b < batch; ++b)
     for (int i = 0; i < c.n_out; ++i)

@@ -31,7 +31,7 @@ struct GemmP {
   int ksplit;      // gridDim.y
   int stages;      // smem ring depth
   float* scratch;  // [tiles][ksplit][ncols][128] fp32 partial tiles (ksplit > 1)
-  unsigned* tickets;  // [tiles]
+  unsigned* tickets;  // [256]: arrivals per tile in [0, 128), completions per tile in [128, 256)
   float* out;
   int ldo;
   // G_QKV: KVCache.update scatter (fast_model.py:104-113)
@@ -82,7 +82,6 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int stage_bytes = NA * GEMM_A_BYTES + b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);  // full[S], empty[S], acc_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
-  int* last_flag = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tile = blockIdx.x, split = blockIdx.y;
@@ -207,46 +206,61 @@ k_umma_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
+      // Every split of this tile waits for all of them (grid = tiles x ksplit <= SM count: all co-resident), then reduces
+      // ITS OWN share of the activation rows -- the reduction is spread over the ksplit CTAs instead of serialising
+      // R x ksplit dependent L2 round trips in the last arriver (that was 100 us of a 109 us prefill GEMM).  The
+      // summation order over splits is fixed, so the result stays run-to-run deterministic.
       if (tid == 128) {
-        const unsigned t = atomicAdd(&p.tickets[tile], 1u);
-        *last_flag = (t == (unsigned)p.ksplit - 1u);
+        atomicAdd(&p.tickets[tile], 1u);
+        const long long t0 = clock64();
+        unsigned v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.tickets + tile) : "memory");
+          if (clock64() - t0 > 4000000000ll) __trap();
+        } while (v < (unsigned)p.ksplit);
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (*last_flag) {
-        __threadfence();
+      {
+        const int r_lo = (int)(((long long)split * p.R) / p.ksplit), r_hi = (int)(((long long)(split + 1) * p.R) / p.ksplit);
         const float* base = p.scratch + ((size_t)tile * p.ksplit * ncols) * 128 + row_local;
-        // 8 activation rows at a time: all loads of a group are independent and issued back to back
-        // (the serial version was latency-bound: R * ksplit dependent L2 round trips); the summation order over
-        // splits stays fixed -> run-to-run deterministic.
-        for (int n0 = 0; n0 < p.R; n0 += 8) {
-          float y[8], y3[8];
+        for (int n0 = r_lo; n0 < r_hi; n0 += 2) {     // 2 rows x ksplit splits x {hi, lo} (x 2 matrices) loads in flight
+          float y[2] = {0.f, 0.f}, y3[2] = {0.f, 0.f};
+          for (int s0 = 0; s0 < p.ksplit; s0 += 8) {
+            float a[2][8], al[2][8], b3[2][8], bl[2][8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) y[i] = y3[i] = 0.f;
-          for (int s = 0; s < p.ksplit; ++s) {
-            const float* ps = base + ((size_t)s * ncols) * 128;
-            float a[8], al[8], b3[8], bl[8];
+            for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int n = n0 + i;
-              const bool ok = n < p.R;
-              a[i] = ok ? __ldcg(ps + (size_t)n * 128) : 0.f;
-              al[i] = (ok && p.split_lo) ? __ldcg(ps + (size_t)(p.Rpad + n) * 128) : 0.f;
-              if (NA == 2) {
-                b3[i] = ok ? __ldcg(ps + (size_t)(p.NB + n) * 128) : 0.f;
-                bl[i] = (ok && p.split_lo) ? __ldcg(ps + (size_t)(p.NB + p.Rpad + n) * 128) : 0.f;
+              for (int q = 0; q < 8; ++q) {
+                const int n = n0 + i, sp = s0 + q;
+                const bool ok = n < r_hi && sp < p.ksplit;
+                const float* ps = base + ((size_t)sp * ncols) * 128;
+                a[i][q] = ok ? __ldcg(ps + (size_t)n * 128) : 0.f;
+                al[i][q] = (ok && p.split_lo) ? __ldcg(ps + (size_t)(p.Rpad + n) * 128) : 0.f;
+                if (NA == 2) {
+                  b3[i][q] = ok ? __ldcg(ps + (size_t)(p.NB + n) * 128) : 0.f;
+                  bl[i][q] = (ok && p.split_lo) ? __ldcg(ps + (size_t)(p.NB + p.Rpad + n) * 128) : 0.f;
+                }
               }
-            }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              y[i] += a[i] + al[i];
-              if (NA == 2) y3[i] += b3[i] + bl[i];
-            }
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                y[i] += a[i][q] + al[i][q];
+                if (NA == 2) y3[i] += b3[i][q] + bl[i][q];
+              }
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (n0 + i < p.R && j < p.M) gemm_apply<EPI>(p, n0 + i, j, y[i], y3[i]);
+          for (int i = 0; i < 2; ++i)
+            if (n0 + i < r_hi && j < p.M) gemm_apply<EPI>(p, n0 + i, j, y[i], y3[i]);
         }
-        if (tid == 128) p.tickets[tile] = 0u;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (tid == 128) {                       // the split that finishes last re-arms both counters for the next launch
+        const unsigned t = atomicAdd(&p.tickets[128 + tile], 1u);
+        if (t == (unsigned)p.ksplit - 1u) {
+          p.tickets[128 + tile] = 0u;
+          p.tickets[tile] = 0u;
+        }
       }
     }
     ptx::tc_fence_before();

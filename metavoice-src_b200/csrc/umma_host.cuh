@@ -52,8 +52,9 @@ static inline GemmPlan plan_gemm(int M, int K, int NB, bool swiglu, int n_sm) {
   const int nkb = K / 64;
   int ks = n_sm / g.tiles;
   if (ks < 1) ks = 1;
-  if (ks > nkb) ks = nkb;
+  if (ks > nkb / 2) ks = nkb / 2 > 0 ? nkb / 2 : 1;   // at least two k-blocks per split: tiny K is latency-, not bandwidth-bound
   if (ks > 16) ks = 16;
+  if (g.tiles > 128) ks = 1;                           // (the split-K arrival counters cover 128 tiles)
   g.ksplit = ks;
   const int stage_bytes = (swiglu ? 2 : 1) * GEMM_A_BYTES + NB * 128;
   int st = (200 * 1024) / stage_bytes;

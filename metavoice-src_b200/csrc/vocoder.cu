@@ -5,7 +5,8 @@
 // (the reference forces fp32 autocast for the vocoder, decoders.py:84).
 //
 // Activations are [C][T] fp32 per utterance (time contiguous): every conv streams its input window through a
-// shared-memory line buffer with 128-bit coalesced loads and keeps an 8-channel x 4-sample register tile per thread.
+// shared-memory line buffer (128-bit coalesced loads of the tile body, scalar loads for the K-1 halo samples), keeps an
+// 8-channel x 4-sample register tile per thread and writes it back with 128-bit stores.
 #include <cuda_runtime.h>
 
 #include <vector>
@@ -66,9 +67,26 @@ __global__ void __launch_bounds__(256) k_conv1d(const float* __restrict__ x, int
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int c0 = 0; c0 < Cin; c0 += CI) {
     __syncthreads();
-    // line buffer: samples t0-(K-1) .. t0+TT-1 of 16 channels; negative times reflect (x[-j] = x[j])
-    for (int i = threadIdx.x; i < CI * (TT + K - 1); i += 256) {
-      const int ci = i / (TT + K - 1), tt = i - ci * (TT + K - 1);
+    // line buffer: samples t0-(K-1) .. t0+TT-1 of 16 channels.  The TT-sample body is streamed with 128-bit loads
+    // (rows are 16-byte aligned when T % 4 == 0, which holds for every layer of the decoder: T = frames x 8 x ...);
+    // the K-1 halo samples in front are loaded one by one, negative times reflect (x[-j] = x[j]).
+    const bool vec = (T & 3) == 0;
+    if (vec) {
+      for (int i = threadIdx.x; i < CI * (TT / 4); i += 256) {
+        const int ci = i / (TT / 4), q4 = i - ci * (TT / 4);
+        const int t = t0 + 4 * q4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + ci < Cin && t < T) {          // T % 4 == 0: a float4 is either fully inside or fully outside
+          v = *reinterpret_cast<const float4*>(xb + (size_t)(c0 + ci) * T + t);
+          if (elu_in) { v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w); }
+        }
+        float* d = &xs[ci][K - 1 + 4 * q4];
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+      }
+    }
+    for (int i = threadIdx.x; i < CI * (vec ? K - 1 : TT + K - 1); i += 256) {
+      const int span = vec ? K - 1 : TT + K - 1;
+      const int ci = i / span, tt = i - ci * span;
       int t = t0 + tt - (K - 1);
       if (t < 0) t = -t;
       float v = 0.f;
@@ -103,6 +121,14 @@ __global__ void __launch_bounds__(256) k_conv1d(const float* __restrict__ x, int
     const int co = co0 + ty * 8 + i;
     if (co >= Cout) continue;
     const float bv = bias ? bias[co] : 0.f;
+    const int tb = t0 + tx * 4;
+    if (((T & 3) == 0) && tb < T) {            // 128-bit coalesced store of the thread's 4 consecutive samples
+      float4* o = reinterpret_cast<float4*>(y + ((size_t)b * Cout + co) * T + tb);
+      float4 v = make_float4(acc[i][0] + bv, acc[i][1] + bv, acc[i][2] + bv, acc[i][3] + bv);
+      if (accumulate) { const float4 p = *o; v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
+      *o = v;
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int t = t0 + tx * 4 + j;

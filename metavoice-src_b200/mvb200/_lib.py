@@ -37,6 +37,14 @@ class VocConfig(C.Structure):
                 ("compress", C.c_int32), ("max_frames", C.c_int32)]
 
 
+class MbdConfig(C.Structure):
+    _fields_ = [("n_models", C.c_int32), ("chin", C.c_int32), ("hidden", C.c_int32), ("depth", C.c_int32), ("res_blocks", C.c_int32),
+                ("norm_groups", C.c_int32), ("kernel", C.c_int32), ("stride", C.c_int32), ("growth", C.c_float),
+                ("emb_all_layers", C.c_int32), ("codec_dim", C.c_int32), ("num_steps", C.c_int32), ("n_calls", C.c_int32),
+                ("noise_scale", C.c_float), ("clip", C.c_float), ("proc_bands", C.c_int32), ("proc_taps", C.c_int32),
+                ("eq_bands", C.c_int32), ("eq_taps", C.c_int32), ("max_samples", C.c_int32)]
+
+
 class SpkConfig(C.Structure):
     _fields_ = [("n_mels", C.c_int32), ("hidden", C.c_int32), ("n_layers", C.c_int32), ("emb", C.c_int32), ("n_fft", C.c_int32),
                 ("hop", C.c_int32), ("partial_frames", C.c_int32), ("max_samples", C.c_int32)]
@@ -81,6 +89,12 @@ SIGNATURES = {
     "mvb_voc_destroy": (C.c_int, [C.c_void_p]),
     "mvb_voc_decode_latent": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "mvb_voc_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mvb_mbd_workspace_bytes": (C.c_size_t, [C.POINTER(MbdConfig)]),
+    "mvb_mbd_create": (C.c_int, [C.POINTER(MbdConfig), C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.c_void_p,
+                                 C.POINTER(C.c_void_p)]),
+    "mvb_mbd_destroy": (C.c_int, [C.c_void_p]),
+    "mvb_mbd_tokens_to_wav": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64,
+                                        C.c_void_p, C.c_void_p]),
     "mvb_spk_workspace_bytes": (C.c_size_t, [C.POINTER(SpkConfig)]),
     "mvb_spk_create": (C.c_int, [C.POINTER(SpkConfig), C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.c_void_p,
                                  C.POINTER(C.c_void_p)]),

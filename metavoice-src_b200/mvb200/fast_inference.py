@@ -6,8 +6,9 @@ contract (fast_inference.py:41-50, 111-119, 195).  Differences, all stated where
   * the speaker reference may be a RIFF/WAVE file (>= 30 s, utils.py:55-70), embedded by the on-device speaker encoder
     (mvb200/speaker_encoder.py) and disk-cached like the reference (inference.py:419-435), or an already
     computed embedding (``.pt`` tensor / ``.npy``); mp3 / flac / URLs need a decoder / network that this image lacks;
-  * the vocoder stage is the EnCodec decoder; the multi-band-diffusion refinement and the DeepFilterNet enhancer
-    (decoders.py:85, fast_inference.py:158-163) are not implemented (unpinned third-party code, SURVEY.md §8c / N1);
+  * the vocoder stage is the EnCodec decoder followed by the multi-band-diffusion refinement (mvb200/mbd.py; parity
+    UNPINNED, its configuration is read from ``multiband_diffusion.pt`` in the model directory or passed in) when such a
+    checkpoint is available; the DeepFilterNet enhancer (fast_inference.py:158-163) is not implemented (N1);
   * the wav goes through the reference's ``audio_write`` post-processing (loudness normalisation to -14 LUFS, tanh
     compressor, PCM16; decoders.py:40-47) in mvb200/audio_out.py.
 """
@@ -68,7 +69,8 @@ class TTS:
 
     def __init__(self, model_name: str = "metavoiceio/metavoice-1B-v0.1", *, seed: int = 1337, output_dir: str = "outputs",
                  quantisation_mode: Optional[Literal["int4", "int8"]] = None, first_stage_path: Optional[str] = None,
-                 telemetry_origin: Optional[str] = None, encodec_state_dict=None, device: str = "cuda", max_utts: int = 1):
+                 telemetry_origin: Optional[str] = None, encodec_state_dict=None, device: str = "cuda", max_utts: int = 1,
+                 mbd_checkpoint: Optional[dict] = None, mbd_settings=None):
         self._device = device
         self._model_dir = model_name
         if not os.path.isdir(model_name):
@@ -84,6 +86,15 @@ class TTS:
         if encodec_state_dict is None:
             encodec_state_dict = torch.load(f"{self._model_dir}/encodec_24khz.pt", map_location="cpu", weights_only=False)
         self.codec = EncodecDecodeEngine(encodec_state_dict, device=device)
+        # decoders.py:13: MultiBandDiffusion.get_mbd_24khz(bw=6) -- here: {"models", "proc", "settings"} (see mvb200/mbd.py)
+        self.mbd = None
+        mbd_path = f"{self._model_dir}/multiband_diffusion.pt"
+        if mbd_checkpoint is None and os.path.isfile(mbd_path):
+            mbd_checkpoint = torch.load(mbd_path, map_location="cpu", weights_only=False)
+            mbd_settings = mbd_settings or mbd_checkpoint.get("settings")
+        if mbd_checkpoint is not None:
+            from .mbd import MBDSettings, MultiBandDiffusionEngine
+            self.mbd = MultiBandDiffusionEngine(mbd_checkpoint, mbd_settings or MBDSettings(), device=device, max_seconds=30.0)
         self.precision = torch.bfloat16
         self.model, self.tokenizer, self.smodel, self.model_size = build_model(
             precision=self.precision, checkpoint_path=Path(self._first_stage_ckpt),
@@ -105,7 +116,7 @@ class TTS:
         codes = self.llm_second_stage.non_causal_sample(
             texts=[text], encodec_tokens=[torch.tensor(extracted, dtype=torch.int32).unsqueeze(0)],
             speaker_embs=spk_emb.unsqueeze(0), batch_size=1, top_k=200, temperature=1.0)[0]
-        wav = self.codec.decode(codes)
+        wav = self._tokens_to_wav(codes)
         if wav.shape[-1] < 9600:
             raise Exception("wav predicted is shorter than 400ms!")                    # decoders.py:88-91
         name = f"synth_{datetime.now().strftime('%y-%m-%d--%H-%M-%S')}_{text.replace(' ', '_')[:25]}_{uuid.uuid4()}"
@@ -118,6 +129,14 @@ class TTS:
         print(f"\nTotal time to synth (s): {dt}")
         print(f"Real-time factor: {dt / dur:.2f}")
         return path
+
+    def _tokens_to_wav(self, codes: torch.Tensor) -> torch.Tensor:
+        """decoders.py:84-85 ``mbd.tokens_to_wav(tokens)``: codec decode, then (when a diffusion checkpoint is loaded) the
+        multi-band-diffusion refinement conditioned on the codec latent and re-equalised against the codec waveform."""
+        wav = self.codec.decode(codes)
+        if self.mbd is not None:
+            wav = self.mbd.tokens_to_wav(self.codec.decode_latent(codes), wav)
+        return wav
 
     def synthesise_long(self, text: str, spk_ref_path: str, top_p=0.95, guidance_scale=3.0, temperature=1.0,
                         max_chars: int = 220) -> str:
@@ -142,7 +161,7 @@ class TTS:
             codes = self.llm_second_stage.non_causal_sample(
                 texts=[c], encodec_tokens=[torch.tensor(extracted, dtype=torch.int32).unsqueeze(0)],
                 speaker_embs=spk_emb.unsqueeze(0), batch_size=1, top_k=200, temperature=1.0)[0]
-            wavs.append(self.codec.decode(codes).reshape(-1))
+            wavs.append(self._tokens_to_wav(codes).reshape(-1))
         wav = torch.cat(wavs)
         if wav.shape[-1] < 9600:
             raise Exception("wav predicted is shorter than 400ms!")                    # decoders.py:88-91

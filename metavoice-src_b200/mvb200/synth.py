@@ -298,3 +298,53 @@ def synthetic_waveform(seconds: float, sr: int, seed: int = 5):
     env = 0.5 * (1 + np.sin(2 * np.pi * 2.3 * t)) * (0.6 + 0.4 * np.sin(2 * np.pi * 0.31 * t + 1.0))
     sig = sig * env + 0.02 * rng.standard_normal(n)
     return (0.3 * sig / np.abs(sig).max()).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------ multi-band diffusion
+def mbd_checkpoint(cfg, seed: int = 0) -> dict:
+    """Synthetic multi-band-diffusion checkpoint for a parametrised config (oracle/mbd_port.MBDConfig): per band model a
+    DiffusionUnet state dict with audiocraft's module names (models/unet.py) and MultiBandProcessor statistics.  Weights
+    are scaled by 1/sqrt(fan_in) so that activations stay O(1) through the 20-step sampler."""
+    gen = torch.Generator().manual_seed(seed)
+    u = cfg.unet
+    ch = u.channels()
+    rn = lambda *shape, std=1.0: torch.randn(*shape, generator=gen) * std
+    models, proc = [], []
+    for _ in range(cfg.n_models):
+        sd: Dict[str, torch.Tensor] = {}
+
+        def res(prefix, C):
+            for n in ("1", "2"):
+                sd[f"{prefix}norm{n}.weight"] = 1.0 + 0.1 * rn(C)
+                sd[f"{prefix}norm{n}.bias"] = 0.1 * rn(C)
+                sd[f"{prefix}conv{n}.weight"] = rn(C, C, 3, std=0.5 / math.sqrt(3 * C))
+                sd[f"{prefix}conv{n}.bias"] = 0.05 * rn(C)
+
+        cin = u.chin
+        for i, C in enumerate(ch):
+            p = f"encoders.{i}."
+            sd[p + "conv.weight"] = rn(C, cin, u.kernel, std=1.0 / math.sqrt(cin * u.kernel))
+            sd[p + "norm.weight"] = 1.0 + 0.1 * rn(C)
+            sd[p + "norm.bias"] = 0.1 * rn(C)
+            for j in range(u.res_blocks):
+                res(f"{p}res_blocks.{j}.", C)
+            if i == 0:
+                sd["embedding.weight"] = 0.3 * rn(u.num_steps, C)
+            elif u.emb_all_layers:
+                sd[f"embeddings.{i - 1}.weight"] = 0.3 * rn(u.num_steps, C)
+            cin = C
+        sd["conv_codec.weight"] = rn(ch[-1], u.codec_dim, 1, std=1.0 / math.sqrt(u.codec_dim))
+        sd["conv_codec.bias"] = 0.05 * rn(ch[-1])
+        for i in range(u.depth):
+            lvl = u.depth - 1 - i
+            C, cout = ch[lvl], (u.chin if lvl == 0 else ch[lvl - 1])
+            p = f"decoders.{i}."
+            for j in range(u.res_blocks):
+                res(f"{p}res_blocks.{j}.", C)
+            sd[p + "norm.weight"] = 1.0 + 0.1 * rn(C)
+            sd[p + "norm.bias"] = 0.1 * rn(C)
+            sd[p + "convtr.weight"] = rn(C, cout, u.kernel, std=1.0 / math.sqrt(2 * C))
+        models.append(sd)
+        proc.append(dict(mean=0.01 * rn(cfg.proc_bands), std=1.0 + 0.2 * torch.rand(cfg.proc_bands, generator=gen),
+                         target_std=1.0 + 0.2 * torch.rand(cfg.proc_bands, generator=gen)))
+    return dict(models=models, proc=proc)

@@ -54,7 +54,13 @@ def test_tts_wav_speaker_reference_and_long_form(tmp_path, monkeypatch):
                             22050, strategy="clip")
     short = A.audio_write_wav(str(tmp_path / "short_ref"), torch.from_numpy(synth.synthetic_waveform(3.0, 22050, seed=9))[None],
                               22050, strategy="clip")
-    tts = TTS(str(snap), output_dir=str(tmp_path / "out"), encodec_state_dict=enc_sd, device="cuda:0", max_utts=3)
+    from mvb200.mbd import MBDSettings, UnetSettings
+    from oracle import mbd_port as M
+    small = M.MBDConfig(n_models=2, unet=M.UnetCfg(hidden=16, depth=2, growth=2.0), proc_bands=4, eq_bands=8, step_list=[999, 499, 0])
+    mbd_settings = MBDSettings(n_models=2, unet=UnetSettings(hidden=16, depth=2, growth=2.0), proc_bands=4, eq_bands=8, step_list=[999, 499, 0])
+    tts = TTS(str(snap), output_dir=str(tmp_path / "out"), encodec_state_dict=enc_sd, device="cuda:0", max_utts=3,
+              mbd_checkpoint=synth.mbd_checkpoint(small, 0), mbd_settings=mbd_settings)      # vocoder = EnCodec decode + MBD refinement
+    assert tts.mbd is not None
     tts.model._cfg.max_new = 256
     with pytest.raises(Exception, match="too short"):
         tts.synthesise("hi", short)

@@ -62,3 +62,23 @@ def test_stage2_batch_and_pipeline_shapes():
     assert [o.shape[1] for o in out] <= [40, 55, 30] and all(int(o.max()) < 1024 for o in out)
     # rows of a batch are independent: utterance 0 alone gives the same first two (input) codebooks and same length rule
     assert torch.equal(out[0][:2], codes[0][0][:, :out[0].shape[1]])
+
+
+def test_stage2_graph_replay_equals_eager_launches(monkeypatch):
+    """The forward pass is replayed as one CUDA graph (sampling parameters live in device memory): same seed -> the same
+    tokens as the eager launch sequence, for two different seeds / temperatures through the same captured graph."""
+    from mvb200.second_stage import SecondStage
+    d = synth.S2_TINY
+    ck = synth.stage2_checkpoint(d, 1)
+    text, cb0, cb1 = synth.synthetic_stage2_input(d, 50)
+    graph = SecondStage(ck, device="cuda:0")
+    monkeypatch.setenv("MVB_S2_NO_GRAPH", "1")
+    eager = SecondStage(ck, device="cuda:0")
+    monkeypatch.delenv("MVB_S2_NO_GRAPH")
+    idx = graph.build_input(text, [cb0, cb1])[None]
+    spk = synth.synthetic_speaker(seed=2)[None]
+    for seed, temp in ((7, 1.0), (8, 0.7), (7, 1.0)):
+        a = graph.forward_tokens(idx, spk, temp, 200, seed=seed).cpu()
+        b = eager.forward_tokens(idx, spk, temp, 200, seed=seed).cpu()
+        assert torch.equal(a, b)
+    assert not torch.equal(graph.forward_tokens(idx, spk, 1.0, 200, seed=7).cpu(), graph.forward_tokens(idx, spk, 1.0, 200, seed=9).cpu())

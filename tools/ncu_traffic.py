@@ -24,7 +24,7 @@ def val(metric):
 
 rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
 res = {"dram_bytes_per_position": (rd + wr) / n_pos, "dram_read_bytes": rd, "dram_write_bytes": wr, "positions": n_pos,
-       "duration_us": float(rec[col["gpu__time_duration.sum"]].replace(",", "")) if "gpu__time_duration.sum" in col else None,
+       "duration": rec[col["gpu__time_duration.sum"]] + " " + units[col["gpu__time_duration.sum"]] if "gpu__time_duration.sum" in col else None,
        "source": f"ncu --set full --clock-control none, one k_decode_persistent launch of {n_pos} positions at context ~50 (tools/prof_decode.py 1 {n_pos})"}
 json.dump(res, open(out, "w"), indent=1)
 print(json.dumps(res))
