@@ -13,11 +13,14 @@
 // (julius.SplitBands: windowed-sinc low-pass banks, 629 / 2893 taps) are direct FIR kernels.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
 #include "../../include/mvb200.h"
 #include "common.cuh"
+#include "mbd_tc.cuh"
+#include "umma_host.cuh"
 
 using namespace mvb;
 namespace mvb { int set_error(int code, const char* fmt, ...); }
@@ -31,14 +34,17 @@ namespace mvb { int set_error(int code, const char* fmt, ...); }
 
 namespace {
 
-// ---- GroupNorm statistics: stats[2g] = mean, stats[2g+1] = 1/sqrt(var + eps) over (C/groups) x T  (nn.GroupNorm, biased variance)
-__global__ void __launch_bounds__(256) k_gn_stats(const float* __restrict__ x, int C, int T, int groups, float eps, float* __restrict__ stats) {
+// ---- GroupNorm statistics: stats[2g] = mean, stats[2g+1] = 1/sqrt(var + eps) over (C/groups) x T  (nn.GroupNorm, biased variance).
+// Two stages so that a 4-group norm still fills the machine: GN_SPLIT CTAs per group write fp64 partial sums, one small CTA
+// adds them in a fixed order (run-to-run deterministic).
+constexpr int GN_SPLIT = 64;
+__global__ void __launch_bounds__(256) k_gn_partial(const float* __restrict__ x, size_t n, double* __restrict__ part) {
   __shared__ double rs[8], rq[8];
-  const int g = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const size_t n = (size_t)(C / groups) * T;
+  const int g = blockIdx.x, sp = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const float* p = x + (size_t)g * n;
+  const size_t lo = n * sp / GN_SPLIT, hi = n * (sp + 1) / GN_SPLIT;
   double s = 0.0, q = 0.0;
-  for (size_t i = tid; i < n; i += 256) {
+  for (size_t i = lo + tid; i < hi; i += 256) {
     const double v = p[i];
     s += v;
     q += v * v;
@@ -53,10 +59,18 @@ __global__ void __launch_bounds__(256) k_gn_stats(const float* __restrict__ x, i
   if (tid == 0) {
     double S = 0.0, Q = 0.0;
     for (int i = 0; i < 8; ++i) { S += rs[i]; Q += rq[i]; }
-    const double mean = S / (double)n, var = Q / (double)n - mean * mean;
-    stats[2 * g] = (float)mean;
-    stats[2 * g + 1] = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps));
+    part[2 * (g * GN_SPLIT + sp)] = S;
+    part[2 * (g * GN_SPLIT + sp) + 1] = Q;
   }
+}
+__global__ void k_gn_final(const double* __restrict__ part, int groups, double n, float eps, float* __restrict__ stats) {
+  const int g = threadIdx.x;
+  if (g >= groups) return;
+  double S = 0.0, Q = 0.0;
+  for (int i = 0; i < GN_SPLIT; ++i) { S += part[2 * (g * GN_SPLIT + i)]; Q += part[2 * (g * GN_SPLIT + i) + 1]; }
+  const double mean = S / n, var = Q / n - mean * mean;
+  stats[2 * g] = (float)mean;
+  stats[2 * g + 1] = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps));
 }
 
 struct ConvP {
@@ -337,6 +351,10 @@ struct mvb_mbd {
   char* ws;
   std::vector<int> ch;       // channels per level
   int per_model = 0;         // tensors per band model
+  // tensor-core path (mbd_tc.cuh): packed bf16 taps + their tensor maps, by weight tensor index
+  struct TcW { CUtensorMap tmA; int Cin, Cout, K; };
+  std::vector<int> tc_of;    // [n tensors] -> index into tcw, or -1 (CUDA-core path)
+  std::vector<TcW> tcw;
   const float* w(int i) const { return reinterpret_cast<const float*>(arena + off[i]); }
 };
 
@@ -360,8 +378,36 @@ static int mbd_validate(const mvb_mbd_config* c) {
 static int mbd_per_model(const mvb_mbd_config* c) { return c->depth * (3 + 8 * c->res_blocks + 1) + 2 + c->depth * (8 * c->res_blocks + 3) + 2; }
 
 struct MbdWs {
-  size_t cur, est, noise, wav, cond, gn, stdv, low, skip[8], tmp[3], total;
+  size_t cur, est, noise, wav, cond, gn, gn_part, stdv, low, skip[8], tmp[3], xt_hi, xt_lo, wpack, total;
 };
+// Convolutions of one band model in tensor order: fn(tensor index relative to the model, Cin, Cout, K, transposed)
+template <class F>
+static void mbd_for_each_conv(const mvb_mbd_config* c, F fn) {
+  std::vector<int> ch;
+  int h = c->hidden;
+  for (int i = 0; i < c->depth; ++i) { ch.push_back(h); h = (int)(h * c->growth); }
+  int ti = 0, cin = c->chin;
+  for (int i = 0; i < c->depth; ++i) {
+    fn(ti, cin, ch[i], c->kernel, 0);
+    ti += 3;
+    for (int j = 0; j < c->res_blocks; ++j) { fn(ti + 8 * j + 2, ch[i], ch[i], 3, 0); fn(ti + 8 * j + 6, ch[i], ch[i], 3, 0); }
+    ti += 8 * c->res_blocks + 1;
+    cin = ch[i];
+  }
+  ti += 2;
+  for (int i = 0; i < c->depth; ++i) {
+    const int lvl = c->depth - 1 - i;
+    for (int j = 0; j < c->res_blocks; ++j) { fn(ti + 8 * j + 2, ch[lvl], ch[lvl], 3, 0); fn(ti + 8 * j + 6, ch[lvl], ch[lvl], 3, 0); }
+    ti += 8 * c->res_blocks;
+    fn(ti + 2, ch[lvl], lvl == 0 ? c->chin : ch[lvl - 1], c->kernel, 1);
+    ti += 3;
+  }
+}
+static bool mbd_tc_eligible(int cin) { return cin >= 64 && cin % 64 == 0; }
+static bool mbd_tc_enabled() {
+  const char* e = getenv("MVB_MBD_NO_TC");
+  return !(e && e[0] == '1');
+}
 static MbdWs mbd_layout(const mvb_mbd_config* c) {
   MbdWs L{};
   size_t o = 0;
@@ -382,11 +428,22 @@ static MbdWs mbd_layout(const mvb_mbd_config* c) {
   if (tmpsz < T + 64) tmpsz = T + 64;
   L.cond = take((size_t)(h / (int)c->growth) * (c->max_samples / 320 + 8) * 4);
   L.gn = take(4096);
+  L.gn_part = take((size_t)64 * GN_SPLIT * 16);
   L.stdv = take(4096);
   const int fb = (c->eq_bands > c->proc_bands ? c->eq_bands : c->proc_bands);
   L.low = take((size_t)2 * fb * T * 4);
   for (int i = 0; i < c->depth; ++i) L.skip[i] = take(lev[i] * 4);
   for (int i = 0; i < 3; ++i) L.tmp[i] = take(tmpsz * 4);
+  // time-major bf16 copies of one layer input (hi / lo) and the packed bf16 taps of every tensor-core convolution
+  const size_t xt = (big + (size_t)h * (c->stride + 32)) * 2;
+  L.xt_hi = take(xt);
+  L.xt_lo = take(xt);
+  size_t wp = 0;
+  if (mbd_tc_enabled())
+    mbd_for_each_conv(c, [&](int, int cin, int cout, int k, int) {
+      if (mbd_tc_eligible(cin)) wp += ((size_t)k * cout * cin * 2 + 255) / 256 * 256;
+    });
+  L.wpack = take(wp * c->n_models + 256);
   L.total = o;
   return L;
 }
@@ -411,6 +468,32 @@ extern "C" int mvb_mbd_create(const mvb_mbd_config* cfg, const void* d_arena, si
   h->ws = reinterpret_cast<char*>(d_ws);
   int c = cfg->hidden;
   for (int i = 0; i < cfg->depth; ++i) { h->ch.push_back(c); c = (int)(c * cfg->growth); }
+  // tensor-core path: repack the taps of every eligible convolution to bf16 [tap][Cout][Cin] and build their A maps
+  h->tc_of.assign(n_off, -1);
+  if (mbd_tc_enabled() && encode_tiled_fn()) {
+    const MbdWs L = mbd_layout(cfg);
+    size_t wo = 0;
+    bool ok = true;
+    for (int m = 0; m < cfg->n_models && ok; ++m)
+      mbd_for_each_conv(cfg, [&](int ti, int cin, int cout, int k, int tr) {
+        if (!ok || !mbd_tc_eligible(cin)) return;
+        const int gi = m * h->per_model + ti;
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(h->ws + L.wpack + wo);
+        k_mbd_pack_w<<<148 * 4, 256>>>(h->w(gi), cout, cin, k, tr, dst);
+        mvb_mbd::TcW w{};
+        w.Cin = cin; w.Cout = cout; w.K = k;
+        ok = ok && make_tmap_bf16_3d(&w.tmA, dst, (uint64_t)cin, (uint64_t)cout, (uint64_t)k, (uint64_t)cout * cin * 2, 128);
+        h->tc_of[gi] = (int)h->tcw.size();
+        h->tcw.push_back(w);
+        wo += ((size_t)k * cout * cin * 2 + 255) / 256 * 256;
+      });
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mbd_tc_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
+    if (!ok || e != cudaSuccess) {
+      delete h;
+      return mvb::set_error(MVB_ERR_CUDA, "mbd: tensor-core weight repack failed (%s)", ok ? cudaGetErrorString(e) : "tensor map");
+    }
+  }
   *out = h;
   return MVB_OK;
 }
@@ -428,9 +511,57 @@ static int launch_conv(cudaStream_t s, const ConvP& p, int K, int stride) {
   MCK(cudaGetLastError());
   return MVB_OK;
 }
-static int gn_stats(cudaStream_t s, const float* x, int C, int T, int groups, float* stats) {
-  k_gn_stats<<<groups, 256, 0, s>>>(x, C, T, groups, 1e-5f, stats);
+static int gn_stats(mvb_mbd* h, cudaStream_t s, const float* x, int C, int T, int groups, float* stats) {
+  double* part = reinterpret_cast<double*>(h->ws + mbd_layout(&h->cfg).gn_part);
+  const size_t n = (size_t)(C / groups) * T;
+  k_gn_partial<<<dim3(groups, GN_SPLIT), 256, 0, s>>>(x, n, part);
+  k_gn_final<<<1, 64, 0, s>>>(part, groups, (double)n, 1e-5f, stats);
   MCK(cudaGetLastError());
+  return MVB_OK;
+}
+
+// One convolution on the tensor cores (mbd_tc.cuh).  kind 0: Conv1d stride 1 ('same', pad = dil * (K - 1) / 2);
+// 1: Conv1d(K = 2s, stride s, pad s/2) over the right-padded input; 2: ConvTranspose1d(K = 2s, stride s, pad s/2).
+static int launch_conv_tc(mvb_mbd* h, cudaStream_t s, const ConvP& p, int widx, int kind, int K, int stride) {
+  const mvb_mbd::TcW& w = h->tcw[h->tc_of[widx]];
+  const MbdWs L = mbd_layout(&h->cfg);
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(h->ws + L.xt_hi);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(h->ws + L.xt_lo);
+  const int Tpad = kind == 1 ? (p.Tin + stride - 1) / stride * stride : p.Tin;
+  k_mbd_prep_t<<<dim3((Tpad + 31) / 32, (p.Cin + 63) / 64), 256, 0, s>>>(p.x, p.Cin, p.Tin, Tpad, p.gn_stats, p.gn_w, p.gn_b,
+                                                                      p.gn_stats ? p.Cin / p.groups : 1, hi, lo);
+  MCK(cudaGetLastError());
+  const uint64_t rows = kind == 1 ? Tpad / stride : p.Tin, cols = kind == 1 ? (uint64_t)stride * p.Cin : p.Cin;
+  CUtensorMap tBhi, tBlo;
+  if (!make_tmap_bf16(&tBhi, hi, rows, cols, 128) || !make_tmap_bf16(&tBlo, lo, rows, cols, 128))
+    return mvb::set_error(MVB_ERR_CUDA, "mbd: activation tensor map");
+  TcConvP q{};
+  q.Cin = p.Cin; q.M = p.Cout; q.out = p.y; q.ldo = p.Tout; q.bias = p.bias; q.emb = p.emb; q.resid = p.resid;
+  q.Ncols = kind == 2 ? p.Tin : p.Tout;
+  q.ostride = kind == 2 ? stride : 1;
+  TcTaps& t = q.taps;
+  if (kind == 0) {
+    t.n_ph = 1; t.n_slots = K;
+    for (int k = 0; k < K; ++k) { t.a_z[0][k] = k; t.b_shift[0][k] = k * p.dil - p.pad; t.b_col[0][k] = 0; }
+  } else if (kind == 1) {
+    t.n_ph = 1; t.n_slots = K;
+    for (int k = 0; k < K; ++k) {
+      const int o = k - p.pad;
+      const int qd = o >= 0 ? o / stride : -((-o + stride - 1) / stride);
+      t.a_z[0][k] = k; t.b_shift[0][k] = qd; t.b_col[0][k] = (o - qd * stride) * p.Cin;
+    }
+  } else {
+    t.n_ph = stride; t.n_slots = 2;
+    for (int ph = 0; ph < stride; ++ph) {
+      const int e = ph + p.pad;
+      t.a_z[ph][0] = e % stride;          t.b_shift[ph][0] = e / stride;     t.b_col[ph][0] = 0;
+      t.a_z[ph][1] = e % stride + stride; t.b_shift[ph][1] = e / stride - 1; t.b_col[ph][1] = 0;
+    }
+  }
+  const int n_cot = (p.Cout + 127) / 128;
+  k_mbd_tc_conv<<<dim3(t.n_ph * n_cot, (q.Ncols + 127) / 128), 256, TC_SMEM, s>>>(w.tmA, tBhi, tBlo, q);
+  MCK(cudaGetLastError());
+  (void)w.K;
   return MVB_OK;
 }
 
@@ -438,14 +569,14 @@ static int gn_stats(cudaStream_t s, const float* x, int C, int T, int groups, fl
 static int res_block(mvb_mbd* h, cudaStream_t s, int base, int C, int T, int dil, const float* x, float* tmp, float* out, float* stats,
                      const float* emb) {
   ConvP p{};
-  if (int e = gn_stats(s, x, C, T, h->cfg.norm_groups, stats)) return e;
+  if (int e = gn_stats(h, s, x, C, T, h->cfg.norm_groups, stats)) return e;
   p.x = x; p.Cin = C; p.Tin = T; p.w = h->w(base + 2); p.bias = h->w(base + 3); p.y = tmp; p.Cout = C; p.Tout = T; p.dil = dil; p.pad = dil;
   p.gn_stats = stats; p.gn_w = h->w(base); p.gn_b = h->w(base + 1); p.groups = h->cfg.norm_groups;
-  if (int e = launch_conv(s, p, 3, 1)) return e;
-  if (int e = gn_stats(s, tmp, C, T, h->cfg.norm_groups, stats + 64)) return e;
+  if (int e = h->tc_of[base + 2] >= 0 ? launch_conv_tc(h, s, p, base + 2, 0, 3, 1) : launch_conv(s, p, 3, 1)) return e;
+  if (int e = gn_stats(h, s, tmp, C, T, h->cfg.norm_groups, stats + 64)) return e;
   p.x = tmp; p.w = h->w(base + 6); p.bias = h->w(base + 7); p.y = out; p.gn_stats = stats + 64; p.gn_w = h->w(base + 4); p.gn_b = h->w(base + 5);
   p.resid = x; p.emb = emb;
-  return launch_conv(s, p, 3, 1);
+  return h->tc_of[base + 6] >= 0 ? launch_conv_tc(h, s, p, base + 6, 0, 3, 1) : launch_conv(s, p, 3, 1);
 }
 
 // DiffusionUnet.forward (unet.py) for band model m: est <- model(cur, step, cond)
@@ -464,9 +595,9 @@ static int unet_forward(mvb_mbd* h, cudaStream_t s, int m, int step, const float
     const int To = (Tl + c.stride - 1) / c.stride;      // right zero-padding to a multiple of the stride, then k = 2s, p = s/2
     ConvP p{};
     p.x = x; p.Cin = Cin; p.Tin = Tl; p.w = h->w(ti); p.y = tmp[0]; p.Cout = C; p.Tout = To; p.dil = 1; p.pad = pad_k;
-    if (int e = launch_conv(s, p, c.kernel, c.stride)) return e;
+    if (int e = h->tc_of[ti] >= 0 ? launch_conv_tc(h, s, p, ti, 1, c.kernel, c.stride) : launch_conv(s, p, c.kernel, c.stride)) return e;
     // norm -> relu -> res_blocks: the first ResBlock input is relu(GN(conv)); materialise it (it is also the residual)
-    if (int e = gn_stats(s, tmp[0], C, To, G, stats + 128)) return e;
+    if (int e = gn_stats(h, s, tmp[0], C, To, G, stats + 128)) return e;
     k_gn_relu_inplace<<<148 * 4, 256, 0, s>>>(tmp[0], C, To, C / G, stats + 128, h->w(ti + 1), h->w(ti + 2));
     MCK(cudaGetLastError());
     ti += 3;
@@ -515,13 +646,15 @@ static int unet_forward(mvb_mbd* h, cudaStream_t s, int m, int step, const float
       float* t = a; a = b; b = t;
     }
     ti += 8 * c.res_blocks;
-    if (int e = gn_stats(s, a, C, Tsk, G, stats + 128)) return e;
+    if (int e = gn_stats(h, s, a, C, Tsk, G, stats + 128)) return e;
     const int Cout = lvl == 0 ? 1 : h->ch[lvl - 1];
     const int To = Tsk * c.stride;
     ConvP p{};
     p.x = a; p.Cin = C; p.Tin = Tsk; p.w = h->w(ti + 2); p.y = scratch; p.Cout = Cout; p.Tout = To; p.pad = pad_k;
     p.gn_stats = stats + 128; p.gn_w = h->w(ti); p.gn_b = h->w(ti + 1); p.groups = G;
-    if (c.stride == 4) k_mbd_convtr<4><<<dim3((To + 255) / 256, (Cout + 31) / 32), 256, 0, s>>>(p);
+    if (h->tc_of[ti + 2] >= 0) {
+      if (int e = launch_conv_tc(h, s, p, ti + 2, 2, c.kernel, c.stride)) return e;
+    } else if (c.stride == 4) k_mbd_convtr<4><<<dim3((To + 255) / 256, (Cout + 31) / 32), 256, 0, s>>>(p);
     else k_mbd_convtr<2><<<dim3((To + 255) / 256, (Cout + 31) / 32), 256, 0, s>>>(p);
     MCK(cudaGetLastError());
     ti += 3;

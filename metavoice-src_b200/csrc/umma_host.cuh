@@ -39,6 +39,20 @@ static inline bool make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t row
   return r == CUDA_SUCCESS;
 }
 
+// 3-D tensor map over one matrix kind of every layer: dims {K, M, n_layer}, tile {64, 128, 1}, 128B swizzle.
+static inline bool make_tmap_bf16_3d(CUtensorMap* tm, const void* ptr, uint64_t K, uint64_t M, uint64_t L, uint64_t layer_stride_bytes,
+                              uint32_t tile_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {K, M, L};
+  cuuint64_t strides[2] = {K * 2, layer_stride_bytes};
+  cuuint32_t box[3] = {64u, tile_rows, 1};              // rows past M read as zero
+  cuuint32_t estr[3] = {1, 1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct GemmPlan {
   int ksplit, stages;
   size_t smem_bytes, scratch_floats;

@@ -54,3 +54,40 @@ def test_mbd_device_vs_restatement(frames):
     a = eng.tokens_to_wav(cond, wav_e, seed=5).cpu()
     b = eng.tokens_to_wav(cond, wav_e, seed=5).cpu()
     assert torch.equal(a, b) and torch.isfinite(a).all()
+
+
+def _round_conv_weights_to_bf16(ck):
+    for sd in ck["models"]:
+        for k in list(sd):
+            if sd[k].ndim == 3:
+                sd[k] = sd[k].to(torch.bfloat16).to(torch.float32)
+    return ck
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel,stride,frames", [(8, 4, 12), (8, 4, 33), (4, 2, 12)])
+def test_mbd_tensor_core_convs_vs_restatement(kernel, stride, frames):
+    """Channel widths that are multiples of 64 take the tcgen05 path (csrc/mbd_tc.cuh): shifted-GEMM Conv1d (dilation 1
+    and 2), the strided encoder convolution and the phase-decomposed ConvTranspose1d.  With conv weights representable in
+    bf16 the path is exact to fp32 round-off against the fp32 restatement; with arbitrary fp32 weights the only deviation
+    is the bf16 rounding of the taps (reported, bounded)."""
+    from mvb200.mbd import MBDSettings, MultiBandDiffusionEngine, ScheduleSettings, UnetSettings
+    ucfg = dict(hidden=64, depth=2, growth=2.0, kernel=kernel, stride=stride, res_blocks=2, norm_groups=4)
+    cfg = M.MBDConfig(n_models=2, unet=M.UnetCfg(**ucfg), proc_bands=4, eq_bands=8, step_list=[999, 666, 333, 0])
+    settings = MBDSettings(n_models=2, unet=UnetSettings(**ucfg), schedule=ScheduleSettings(), proc_bands=4, eq_bands=8,
+                           step_list=[999, 666, 333, 0])
+    T = frames * 320 - 7                      # not a multiple of the stride: right padding + crop
+    g = torch.Generator().manual_seed(100 + frames)
+    cond = torch.randn(128, frames, generator=g)
+    wav_e = torch.from_numpy(synth.synthetic_waveform(frames * 320 / 24000.0, 24000, seed=4))[:T]
+    noise = torch.randn(2, 3, T, generator=g)
+    for exact in (True, False):
+        ck = synth.mbd_checkpoint(cfg, 1)
+        if exact:
+            ck = _round_conv_weights_to_bf16(ck)
+        eng = MultiBandDiffusionEngine(ck, settings, device="cuda:0", max_seconds=1.0)
+        want = M.MBDOracle(ck, cfg).tokens_to_wav(wav_e, cond, noise)
+        got = eng.tokens_to_wav(cond, wav_e, noise=noise).cpu()
+        err = float((got - want).abs().max() / want.abs().max())
+        print(f"MBD tensor-core (k={kernel}, s={stride}, {T} samples, bf16-representable taps={exact}): rel err {err:.2e}")
+        assert err < (2e-3 if exact else 3e-2)
