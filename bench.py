@@ -52,6 +52,17 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_tensor_peak():
+    """Dense bf16 TFLOP/s: the sustained figure of MEASURED_PEAKS.json (kernels timed inside a long step), else the recipe's fallback."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        try:
+            return float(json.load(open(path))["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+        except Exception:
+            pass
+    return 1590.0, "fallback (B200_PROFILING.md 1.59 PFLOP/s bf16)"
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
 
@@ -406,6 +417,23 @@ def pipeline_leg(model, prompts, spk, h_spk_pinned, utts, steps, device, world, 
     barrier()
     pipe_s = time.perf_counter() - t0
     audio_s, s1_s, s2_s, voc_s, mbd_s, post_s = acc
+    # rooflines of the downstream stages (one utterance): stage-2 streams its bf16 weights once per forward (HBM-bound);
+    # the SEANet decoder is fp32 CUDA-core work; the diffusion UNets are tcgen05 GEMM work (bf16 taps, two-term activations)
+    hbm_peak, tensor_peak = measured_peaks()[0], measured_tensor_peak()[0]
+    n_u = steps * utts
+    s2_bytes = sum(v.numel() for k, v in synth.stage2_checkpoint(synth.S2_FULL, 1)["model"].items() if v.ndim == 2) * 2
+    s2_gbs = s2_bytes / (s2_s / n_u) / 1e9
+    voc_tf = 2 * codec.flops(frames) / (voc_s / n_u) / 1e12      # decode() + decode_latent() per utterance ~ 1 decoder pass + lookup
+    mbd_tf = mbd.flops(frames * 320, frames) / (mbd_s / n_u) / 1e12
+    stage_rooflines = {
+        "stage2": {"bound": "hbm", "achieved": round(s2_gbs, 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(s2_gbs / hbm_peak, 4),
+                   "note": "bf16 weight bytes of one non-causal forward / wall time of build_input + forward + sampling (launch-bound at T = 387)"},
+        "encodec_decoder": {"bound": "fp32", "achieved": round(voc_tf / 2, 2), "unit": "TFLOP/s",
+                            "note": "fp32 FMA FLOPs of the SEANet decoder / wall time of decode + decode_latent"},
+        "multiband_diffusion": {"bound": "tensor", "achieved": round(mbd_tf, 1), "peak": tensor_peak, "unit": "TFLOP/s",
+                                "frac": round(mbd_tf / tensor_peak, 4),
+                                "note": "algorithmic conv FLOPs of 80 UNet passes / wall time of tokens_to_wav (the two-term activation split "
+                                        "doubles the issued MMA work; GroupNorm, transposes, FIR banks and the level-0 CUDA-core convs are in the time)"}}
     mbd.close(); codec.close(); s2.close()
     u = mbd_cfg.unet
     return {"audio_sec_per_s": round(audio_s * world / pipe_s, 3),
@@ -415,7 +443,9 @@ def pipeline_leg(model, prompts, spk, h_spk_pinned, utts, steps, device, world, 
                             "encodec_decoder": round(voc_s / steps * 1e3, 2), "multiband_diffusion": round(mbd_s / steps * 1e3, 2),
                             "audio_post_pcm16": round(post_s / steps * 1e3, 2)},
             "mbd_config": f"PARAMETRISED, parity unpinned: {mbd_cfg.n_models} band UNets (hidden {u.hidden}, depth {u.depth}, growth {u.growth}, "
-                          f"k{u.kernel}/s{u.stride}, {u.res_blocks} res block) x {len(mbd_cfg.steps()) - 1} calls, {mbd_cfg.eq_bands}-band re-EQ, fp32 CUDA-core convolutions",
+                          f"k{u.kernel}/s{u.stride}, {u.res_blocks} res block) x {len(mbd_cfg.steps()) - 1} calls, {mbd_cfg.eq_bands}-band re-EQ; "
+                          "convolutions with >= 64 input channels on tcgen05 (bf16 taps, hi/lo activations), the rest fp32 CUDA-core",
+            "stage_rooflines": stage_rooflines,
             "coverage": "stage-1 (750 tokens) + token adapters + stage-2 (6 codebooks) + EnCodec SEANet decoder + multi-band diffusion "
                         "+ loudness/compressor/PCM16 on device, wav bytes on the host; DeepFilterNet is NOT implemented"}
 

@@ -41,7 +41,7 @@ constexpr int PC_THREADS = 224;      // producer warp + MMA warp + 4 compute war
 constexpr int PC_KV_TILE_BYTES = 16384;   // K (or V) tile of one (row, head): 64 bf16 / 32 fp32 positions
 constexpr int PC_RPAD = 16;          // rows of the fp32 activation buffers (8 utterances x 2 CFG rows)
 constexpr int PC_BKB_MAX = 12;       // k-blocks of the activation operand one CTA may own in a phase
-constexpr int PC_NKV = 2;            // (K tile, V tile) slots
+constexpr int PC_NKV_MAX = 4;        // (K tile, V tile) slots: PcCfg::NKV of them are used
 constexpr int PC_MAX_CHUNKS = 64;    // per (row, head): ceil(2048 / 32) in fp32 mode
 constexpr int PC_TRACE_EVENTS = 512;
 constexpr int PC_MAX_TILES = 128;    // attention KV tiles one CTA may own per layer
@@ -55,7 +55,7 @@ struct AttTile {
 };
 
 struct PcShared {   // small shared state behind the big buffers
-  uint64_t b_full[8], b_empty[8], b_ready, acc_full[2], acc_empty[2], kv_full[PC_NKV], kv_empty[PC_NKV], tab_ready;
+  uint64_t b_full[8], b_empty[8], b_ready, acc_full[2], acc_empty[2], kv_full[PC_NKV_MAX], kv_empty[PC_NKV_MAX], tab_ready;
   uint32_t tmem_slot;
   int prod_pos;                      // weight tiles issued so far (producer -> L2 prefetcher)
   int n_att_tiles;
@@ -81,12 +81,18 @@ struct PcShared {   // small shared state behind the big buffers
 template <int NB, bool WB> struct PcCfg {
   static constexpr int TILE_ROWS = WB ? 256 : 128;
   static constexpr int STAGE_BYTES = TILE_ROWS * 128;     // [TILE_ROWS x 64 k] bf16
+#ifdef PC_DEEP_KV   // A/B: trade weight-ring depth for KV tiles in flight (the attention phase is bound by KV load latency)
+  static constexpr int STAGES = WB ? ((NB == 16) ? 4 : 3) : ((NB == 16) ? 6 : 4);
+  static constexpr int NKV = WB ? 2 : 3;
+#else
   static constexpr int STAGES = WB ? ((NB == 16) ? 4 : 3) : ((NB == 16) ? 8 : 6);
+  static constexpr int NKV = 2;
+#endif
   static constexpr int B_BYTES = PC_BKB_MAX * NB * 128;
   static constexpr int RH = NB / 2;                       // activation rows carried (hi rows; lo rows follow)
   static constexpr int ACC_COLS = WB ? 256 : NB;          // TMEM columns of one accumulator
   static constexpr int TMEM_COLS = WB ? 512 : 64;
-  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + B_BYTES + (size_t)PC_NKV * 2 * PC_KV_TILE_BYTES +
+  static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + B_BYTES + (size_t)NKV * 2 * PC_KV_TILE_BYTES +
                                  sizeof(PcShared) + 64;
 };
 
@@ -278,6 +284,14 @@ __device__ __forceinline__ int build_att_table(const PcParams& p, const int* st_
   return nt;
 }
 
+// e^x on the SFU without the denormal-range fix-up __expf carries (3 extra instructions + predicates per call);
+// ex2.approx.ftz(-inf) = +0, which the attention loop relies on for masked positions.
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+
 template <bool KV_FP32>
 __device__ __forceinline__ void load8s(const uint8_t* tile, int p, int sub, float (&v)[8]) {
   if (KV_FP32) {
@@ -310,7 +324,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   uint8_t* ring = smem;
   uint8_t* Bop = ring + STAGES * STAGE_BYTES;
   uint8_t* kvbuf = Bop + Cfg::B_BYTES;                       // [NKV][K tile | V tile]; sampler scratch between tokens
-  PcShared& sh = *reinterpret_cast<PcShared*>(kvbuf + PC_NKV * 2 * PC_KV_TILE_BYTES);
+  PcShared& sh = *reinterpret_cast<PcShared*>(kvbuf + Cfg::NKV * 2 * PC_KV_TILE_BYTES);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cta = blockIdx.x, G = gridDim.x;
@@ -327,7 +341,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       ptx::mbar_init(ptx::smem_u32(sh.acc_full + i), 1);
       ptx::mbar_init(ptx::smem_u32(sh.acc_empty + i), WB ? 1 : 128);   // WB: one arrive by the TMEM-reading warp
     }
-    for (int i = 0; i < PC_NKV; ++i) {
+    for (int i = 0; i < Cfg::NKV; ++i) {
       ptx::mbar_init(ptx::smem_u32(sh.kv_full + i), 1);
       ptx::mbar_init(ptx::smem_u32(sh.kv_empty + i), 1);
     }
@@ -447,7 +461,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           const int my = idx++;
           if (my < from) continue;
           if (my >= to) break;
-          const uint32_t ks = kv_ctr % PC_NKV, ph = (kv_ctr / PC_NKV) & 1u;
+          const uint32_t ks = kv_ctr % Cfg::NKV, ph = (kv_ctr / Cfg::NKV) & 1u;
           ++kv_ctr;
           ptx::mbar_wait(ptx::smem_u32(sh.kv_empty + ks), ph ^ 1u);
           if (ptx::elect_one()) {
@@ -461,7 +475,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           __syncwarp();
         }
       };
-      // Pull every KV tile this CTA will need for layer l into L2 ahead of time: with only PC_NKV tile slots in shared
+      // Pull every KV tile this CTA will need for layer l into L2 ahead of time: with only Cfg::NKV tile slots in shared
       // memory the attention phase would otherwise pay an HBM round trip per tile (batch 8: 55 MB of K/V per layer).
       auto kv_prefetch_l2 = [&](int l) {
         const char* kbase = p.kv + (size_t)l * 2 * p.kv_half;
@@ -485,14 +499,14 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             ptx::mbar_wait(ptx::smem_u32(&sh.tab_ready), step & 1u);   // this token's tile table is built
             kv_units(0, 0, 1 << 30);
           } else {
-            kv_units(l, PC_NKV, 1 << 30);                       // (units beyond the prefetched ones)
+            kv_units(l, Cfg::NKV, 1 << 30);                       // (units beyond the prefetched ones)
           }
           if (p.kv_pf && l + 1 < p.n_layer) kv_prefetch_l2(l + 1);
           gemm_tiles(&tm_o, &tm_o, 1 << 30, s_o, l);
           gemm_tiles(&tm_w1, &tm_w3, T1, s_w13, l);
           gemm_tiles(&tm_w2, &tm_w2, 1 << 30, s_w2, l);
           if (l + 1 < p.n_layer) {
-            kv_units(l + 1, 0, PC_NKV);                         // next layer's first KV tiles ride ahead of its QKV GEMM
+            kv_units(l + 1, 0, Cfg::NKV);                         // next layer's first KV tiles ride ahead of its QKV GEMM
             gemm_tiles(&tm_qkv, &tm_qkv, 1 << 30, s_qkv, l + 1);
           }
         }
@@ -900,9 +914,14 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           char* vbase = kbase + p.kv_half;
           const int half = lane >> 4, sub = lane & 15;
           const int hw = cw * 2 + half;               // half-warp id 0..7
-          const unsigned hmask = half ? 0xffff0000u : 0x0000ffffu;
           float q[8], o[8], m = -INFINITY, lsum = 0.f, kcur = 0.f, vcur = 0.f;
           const int n_tiles = sh.n_att_tiles;
+#ifdef PC_ATT_PROF
+          long long a_t[5] = {0, 0, 0, 0, 0}, a_c = clock64();   // begin | append cur | kv wait | tile math | unit end
+#define PC_ATT_MARK(k) { const long long _n = clock64(); a_t[k] += _n - a_c; a_c = _n; }
+#else
+#define PC_ATT_MARK(k)
+#endif
           for (int ti = 0; ti < n_tiles; ++ti) {
             const AttTile e = sh.att_tab[ti];
             const int npos = (int)(e.meta & 0xffu);
@@ -930,6 +949,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] = 0.f;
             }
+            PC_ATT_MARK(0)
             // ---- one KV tile (and, on the row's last tile, the current token)
             if (has_cur) {
               // append the new token's k, v to the cache, rounded as the cache stores them; share them via smem
@@ -949,42 +969,55 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
               sh.cur[ct] = kcur;
               sh.cur[128 + ct] = vcur;
             }
+            PC_ATT_MARK(1)
             if (npos > 0) {
-              const uint32_t ks = kv_ctr % PC_NKV, ph = (kv_ctr / PC_NKV) & 1u;
+              const uint32_t ks = kv_ctr % Cfg::NKV, ph = (kv_ctr / Cfg::NKV) & 1u;
               ++kv_ctr;
               ptx::mbar_wait(ptx::smem_u32(sh.kv_full + ks), ph);
+              PC_ATT_MARK(2)
               const uint8_t* kt = kvbuf + (size_t)ks * 2 * PC_KV_TILE_BYTES;
               const uint8_t* vt = kt + PC_KV_TILE_BYTES;
-              // each half-warp owns positions hw, hw+8, ...; two positions per trip for ILP (four per trip was measured:
-              // the extra 32 live registers spill in this 255-register kernel and the phase gets 15-30 % slower)
-              for (int pb = hw; pb < npos; pb += 16) {
-                const int pA = pb, pB = pb + 8;
-                const bool vB = pB < npos;
-                float ka[8], kb2[8], sA = 0.f, sB = 0.f;
+              // each half-warp owns positions hw, hw+8, ... (hw = 2 * warp + half); two positions per trip for ILP (four per
+              // trip was measured: the extra 32 live registers spill in this 255-register kernel and the phase gets 15-30 %
+              // slower).  The trip count is WARP-uniform and out-of-range positions are clamped to position 0 with score -inf
+              // (weight exactly 0): full-mask shuffles (no MATCH.ANY / BRA.DIV convergence checks per shuffle) and no
+              // select between the dependent FMAs of the dot products.
+              for (int pb = cw * 2; pb < npos; pb += 16) {
+                const int pA0 = pb + half, pB0 = pA0 + 8;
+                const bool vA = pA0 < npos, vB = pB0 < npos;
+                const int pA = vA ? pA0 : 0, pB = vB ? pB0 : 0;
+                float ka[8], kb2[8], sA = 0.f, sA1 = 0.f, sB = 0.f, sB1 = 0.f;
                 load8s<KV_FP32>(kt, pA, sub, ka);
-                if (vB) load8s<KV_FP32>(kt, pB, sub, kb2);
+                load8s<KV_FP32>(kt, pB, sub, kb2);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
+                for (int i = 0; i < 8; i += 2) {
                   sA = fmaf(q[i], ka[i], sA);
-                  if (vB) sB = fmaf(q[i], kb2[i], sB);
+                  sA1 = fmaf(q[i + 1], ka[i + 1], sA1);
+                  sB = fmaf(q[i], kb2[i], sB);
+                  sB1 = fmaf(q[i + 1], kb2[i + 1], sB1);
                 }
+                sA += sA1;
+                sB += sB1;
 #pragma unroll
-                for (int off = 8; off > 0; off >>= 1) {   // reduce inside the 16-lane group only: trip counts differ per half-warp
-                  sA += __shfl_xor_sync(hmask, sA, off);
-                  sB += __shfl_xor_sync(hmask, sB, off);
+                for (int off = 8; off > 0; off >>= 1) {   // xor offsets < 16: the reduction stays inside the 16-lane group
+                  sA += __shfl_xor_sync(0xffffffffu, sA, off);
+                  sB += __shfl_xor_sync(0xffffffffu, sB, off);
                 }
                 load8s<KV_FP32>(vt, pA, sub, ka);
-                if (vB) load8s<KV_FP32>(vt, pB, sub, kb2);
-                const float mn = fmaxf(m, vB ? fmaxf(sA, sB) : sA);
-                const float corr = __expf(m - mn), wA = __expf(sA - mn), wB = vB ? __expf(sB - mn) : 0.f;
+                load8s<KV_FP32>(vt, pB, sub, kb2);
+                sA = vA ? sA : -INFINITY;
+                sB = vB ? sB : -INFINITY;
+                const float mn = fmaxf(m, fmaxf(sA, sB));
+                const float mref = (mn == -INFINITY) ? 0.f : mn;          // nothing valid yet: every weight below is exp(-inf) = 0
+                const float corr = fast_exp(m - mref), wA = fast_exp(sA - mref), wB = fast_exp(sB - mref);
                 lsum = lsum * corr + wA + wB;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + wA * ka[i] + (vB ? wB * kb2[i] : 0.f);
+                for (int i = 0; i < 8; ++i) o[i] = fmaf(o[i], corr, fmaf(wA, ka[i], wB * kb2[i]));
                 m = mn;
               }
             }
             if (npos > 0 || has_cur) compute_sync();   // KV tile fully consumed; sh.cur visible
-            if (npos > 0 && ct == 0) ptx::mbar_arrive(ptx::smem_u32(sh.kv_empty + ((kv_ctr - 1) % PC_NKV)));
+            if (npos > 0 && ct == 0) ptx::mbar_arrive(ptx::smem_u32(sh.kv_empty + ((kv_ctr - 1) % Cfg::NKV)));
             if (has_cur && hw == 0) {
               float sdot = 0.f;
 #pragma unroll
@@ -997,6 +1030,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
               for (int i = 0; i < 8; ++i) o[i] = o[i] * corr + pw * sh.cur[128 + sub * 8 + i];
               m = mn;
             }
+            PC_ATT_MARK(3)
             if (unit_last) {
               // ---- unit end: merge the 8 half-warp states -> one partial (m, l, o[128]) for split z
               if (sub == 0) { sh.m[hw] = m; sh.l[hw] = lsum; }
@@ -1021,7 +1055,12 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
               }
               compute_sync();   // sh.o / sh.m / sh.cur are reused by the next unit
             }
+            PC_ATT_MARK(4)
           }
+#ifdef PC_ATT_PROF
+          if (p.trace != nullptr && ct == 0)
+            for (int k = 0; k < 5; ++k) p.trace[(size_t)cta * PC_TRACE_EVENTS + 380 + l * 5 + k] = a_t[k];
+#endif
         }
         stamp();
         grid_arrive();

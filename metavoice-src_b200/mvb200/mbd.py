@@ -157,6 +157,19 @@ class MultiBandDiffusionEngine:
         self._h = h
         self.n_calls = sched.shape[0]
 
+    def flops(self, n_samples: int, n_frames: int) -> float:
+        """FLOPs (2 x multiply-adds) of the convolutions of one ``tokens_to_wav`` call: every band model x every sampler call."""
+        u, ch = self.s.unet, self.s.unet.channels()
+        t, cin, per = n_samples, u.chin, 0.0
+        for c in ch:
+            t = -(-t // u.stride)
+            per += 2.0 * u.kernel * cin * c * t                       # strided encoder conv
+            per += 2 * u.res_blocks * 2 * (2.0 * 3 * c * c * t)       # encoder + decoder ResBlocks (two k = 3 convs each)
+            per += 2.0 * u.kernel * c * cin * t                       # transposed conv back to the level above
+            cin = c
+        per += 2.0 * u.codec_dim * ch[-1] * n_frames
+        return per * self.s.n_models * (len(self.s.steps()) - 1)
+
     def close(self):
         if getattr(self, "_h", None) is not None:
             self._lib.mvb_mbd_destroy(self._h)

@@ -68,6 +68,21 @@ class EncodecDecodeEngine:
         self.upsample = 1
         for r in RATIOS:
             self.upsample *= r
+        # multiply-add accounting for the roofline in bench.py: (weight elements, output-rate multiplier) per layer
+        terms, mult, k = [(tensors[n_q].numel(), 1)], 1, n_q + 2
+        terms += [(tensors[k + 3 * l].numel() + tensors[k + 3 * l + 1].numel(), 1) for l in range(2)]
+        k += 6
+        for r in RATIOS:
+            terms.append((tensors[k].numel(), mult))              # transposed conv: every input sample meets every tap
+            mult *= r
+            terms += [(tensors[k + 2 * j].numel(), mult) for j in (1, 2, 3)]
+            k += 8
+        terms.append((tensors[k].numel(), mult))
+        self._flop_terms = terms
+
+    def flops(self, n_frames: int) -> float:
+        """fp32 FLOPs (2 x multiply-adds) of one SEANet decode of ``n_frames`` code frames."""
+        return float(sum(2.0 * n * m * n_frames for n, m in self._flop_terms))
 
     def close(self):
         if getattr(self, "_h", None) is not None:

@@ -48,3 +48,8 @@ for j, nm in enumerate(names):
     v = per[:, 2:, j]
     print(f"{nm:10s} median {np.median(v):7.2f}  mean {v.mean():7.2f}  p90 {np.percentile(v, 90):7.2f}  max {v.max():7.2f}")
 print("per-layer sum (median CTA):", np.median(per[:, 2:, :].sum(axis=2)))
+sub = buf[:, 380:380 + 5 * 24].astype(np.float64).reshape(148, 24, 5) / 1.9e3
+if sub.any():      # library built with -DPC_ATT_PROF: cumulative attention sub-phase clocks per layer
+    for j, nm in enumerate(["att.begin(q load)", "att.append_cur", "att.kv_wait", "att.tile_math", "att.unit_end"]):
+        v = sub[:, 2:, j]
+        print(f"{nm:18s} median {np.median(v):7.2f}  mean {v.mean():7.2f}  p90 {np.percentile(v, 90):7.2f}  max {v.max():7.2f}")
