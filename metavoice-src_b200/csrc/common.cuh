@@ -8,6 +8,13 @@
 
 namespace mvb {
 
+// cudaFuncSetAttribute applies to the CURRENT device only: remember per (call site, device), not per process.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool pending() const { int d = 0; cudaGetDevice(&d); return d < 0 || d >= 64 || !done[d]; }
+  void mark() { int d = 0; cudaGetDevice(&d); if (d >= 0 && d < 64) done[d] = true; }
+};
+
 // 128-bit streaming load that does not pollute L1 (weights/KV are read exactly once per step).
 __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   uint4 r;

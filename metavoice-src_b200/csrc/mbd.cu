@@ -667,8 +667,8 @@ static int unet_forward(mvb_mbd* h, cudaStream_t s, int m, int step, const float
 
 static int split_lows(mvb_mbd* h, cudaStream_t s, const float* x, int T, int n_bands, const float* bank, int L, float* low) {
   const size_t smem = (size_t)(256 + 2 * L) * 4;
-  static bool attr = false;
-  if (!attr) { MCK(cudaFuncSetAttribute(k_fir_bank, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr = true; }
+  static PerDeviceOnce attr;
+  if (attr.pending()) { MCK(cudaFuncSetAttribute(k_fir_bank, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr.mark(); }
   if (smem > 64 * 1024) return mvb::set_error(MVB_ERR_UNSUPPORTED, "mbd: filter length %d", L);
   k_fir_bank<<<dim3((T + 255) / 256, n_bands - 1), 256, smem, s>>>(x, T, bank, L, low);
   MCK(cudaGetLastError());

@@ -85,11 +85,11 @@ static inline GemmPlan plan_gemm(int M, int K, int NB, bool swiglu, int n_sm) {
 template <int EPI>
 static inline cudaError_t launch_umma_gemm(cudaStream_t s, const CUtensorMap& tA, const CUtensorMap& tA3, const CUtensorMap& tB,
                                            GemmP p, const GemmPlan& g) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.pending()) {
     cudaError_t e = cudaFuncSetAttribute(k_umma_gemm<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set.mark();
   }
   p.ksplit = g.ksplit;
   p.stages = g.stages;

@@ -393,8 +393,8 @@ extern "C" int mvb_voc_decode(mvb_voc* h, const int32_t* d_codes, int32_t T, flo
   ti += 2;
   // LSTM: x = B;  layer 0 -> A ; layer 1 (+ skip x) -> Cc
   const size_t lsmem = (size_t)(16 * top + top) * 4;
-  static bool attr = false;
-  if (!attr) { VCK(cudaFuncSetAttribute(k_lstm_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr = true; }
+  static PerDeviceOnce attr;
+  if (attr.pending()) { VCK(cudaFuncSetAttribute(k_lstm_layer, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr.mark(); }
   const float* lin = B;
   float* louts[2] = {A, Cc};
   for (int l = 0; l < 2; ++l) {
