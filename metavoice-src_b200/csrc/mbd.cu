@@ -63,14 +63,21 @@ __global__ void __launch_bounds__(256) k_gn_partial(const float* __restrict__ x,
     part[2 * (g * GN_SPLIT + sp) + 1] = Q;
   }
 }
+// one warp per group: lane i adds partials i and i + 32, then a fixed-shape butterfly (deterministic)
 __global__ void k_gn_final(const double* __restrict__ part, int groups, double n, float eps, float* __restrict__ stats) {
-  const int g = threadIdx.x;
-  if (g >= groups) return;
+  const int g = blockIdx.x, lane = threadIdx.x;
   double S = 0.0, Q = 0.0;
-  for (int i = 0; i < GN_SPLIT; ++i) { S += part[2 * (g * GN_SPLIT + i)]; Q += part[2 * (g * GN_SPLIT + i) + 1]; }
-  const double mean = S / n, var = Q / n - mean * mean;
-  stats[2 * g] = (float)mean;
-  stats[2 * g + 1] = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps));
+  for (int i = lane; i < GN_SPLIT; i += 32) { S += part[2 * (g * GN_SPLIT + i)]; Q += part[2 * (g * GN_SPLIT + i) + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    S += __shfl_xor_sync(0xffffffffu, S, o);
+    Q += __shfl_xor_sync(0xffffffffu, Q, o);
+  }
+  if (lane == 0) {
+    const double mean = S / n, var = Q / n - mean * mean;
+    stats[2 * g] = (float)mean;
+    stats[2 * g + 1] = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps));
+  }
 }
 
 struct ConvP {
@@ -263,28 +270,48 @@ __global__ void k_randn(float* __restrict__ out, int T, unsigned long long seed,
   }
 }
 
-// julius.LowPassFilters with replicate padding: low[f][t] = sum_j bank[f][j] * x[clamp(t + j - half)].  One CTA = 256 outputs of one filter.
-__global__ void __launch_bounds__(256) k_fir_bank(const float* __restrict__ x, int T, const float* __restrict__ bank, int L, float* __restrict__ low) {
+// julius.LowPassFilters with replicate padding: low[f][t] = sum_j bank[f][j] * x[clamp(t + j - half)].  One CTA = 1024 outputs of two
+// filters: every thread keeps 4 outputs (t, t+256, t+512, t+768) x 2 filters in registers, so one tap costs 4 conflict-free x
+// reads + 2 broadcast coefficient reads for 8 FMAs (the direct form was 2 shared-memory reads per FMA).
+constexpr int FIR_TT = 1024;
+__global__ void __launch_bounds__(256) k_fir_bank(const float* __restrict__ x, int T, const float* __restrict__ bank, int L, int nf,
+                                                  float* __restrict__ low) {
   extern __shared__ float sm[];
-  float* xs = sm;                 // [256 + L - 1]
-  float* fs = sm + 256 + L - 1;   // [L]
-  const int t0 = blockIdx.x * 256, f = blockIdx.y, half = (L - 1) / 2;
-  for (int i = threadIdx.x; i < 256 + L - 1; i += 256) {
+  float* xs = sm;                       // [FIR_TT + L - 1]
+  float* f0s = sm + FIR_TT + L - 1;     // [L]
+  float* f1s = f0s + L;                 // [L]
+  const int t0 = blockIdx.x * FIR_TT, f0 = blockIdx.y * 2, f1 = f0 + 1, half = (L - 1) / 2;
+  const bool two = f1 < nf;
+  for (int i = threadIdx.x; i < FIR_TT + L - 1; i += 256) {
     int t = t0 + i - half;
     t = t < 0 ? 0 : (t >= T ? T - 1 : t);
     xs[i] = x[t];
   }
-  for (int i = threadIdx.x; i < L; i += 256) fs[i] = bank[(size_t)f * L + i];
-  __syncthreads();
-  const int t = t0 + threadIdx.x;
-  float a0 = 0.f, a1 = 0.f;
-  int j = 0;
-  for (; j + 1 < L; j += 2) {
-    a0 = fmaf(fs[j], xs[threadIdx.x + j], a0);
-    a1 = fmaf(fs[j + 1], xs[threadIdx.x + j + 1], a1);
+  for (int i = threadIdx.x; i < L; i += 256) {
+    f0s[i] = bank[(size_t)f0 * L + i];
+    f1s[i] = two ? bank[(size_t)f1 * L + i] : 0.f;
   }
-  if (j < L) a0 = fmaf(fs[j], xs[threadIdx.x + j], a0);
-  if (t < T) low[(size_t)f * T + t] = a0 + a1;
+  __syncthreads();
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* xp = xs + threadIdx.x;
+#pragma unroll 4
+  for (int j = 0; j < L; ++j) {
+    const float c0 = f0s[j], c1 = f1s[j];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xv = xp[j + 256 * k];
+      a[k] = fmaf(c0, xv, a[k]);
+      b[k] = fmaf(c1, xv, b[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int t = t0 + threadIdx.x + 256 * k;
+    if (t < T) {
+      low[(size_t)f0 * T + t] = a[k];
+      if (two) low[(size_t)f1 * T + t] = b[k];
+    }
+  }
 }
 // band b of SplitBands from the low-passed copies: b = 0: low[0]; 0 < b < n-1: low[b] - low[b-1]; b = n-1: x - low[n-2]
 __device__ __forceinline__ float band_at(const float* low, const float* x, int T, int n_bands, int b, int t) {
@@ -403,7 +430,9 @@ static void mbd_for_each_conv(const mvb_mbd_config* c, F fn) {
     ti += 3;
   }
 }
-static bool mbd_tc_eligible(int cin) { return cin >= 64 && cin % 64 == 0; }
+// Input widths >= 32 take the tensor-core path; the time-major copy and the packed taps are zero-padded to a multiple of 64 channels
+static bool mbd_tc_eligible(int cin) { return cin >= 32; }
+static int mbd_tc_cpad(int cin) { return (cin + 63) / 64 * 64; }
 static bool mbd_tc_enabled() {
   const char* e = getenv("MVB_MBD_NO_TC");
   return !(e && e[0] == '1');
@@ -435,13 +464,13 @@ static MbdWs mbd_layout(const mvb_mbd_config* c) {
   for (int i = 0; i < c->depth; ++i) L.skip[i] = take(lev[i] * 4);
   for (int i = 0; i < 3; ++i) L.tmp[i] = take(tmpsz * 4);
   // time-major bf16 copies of one layer input (hi / lo) and the packed bf16 taps of every tensor-core convolution
-  const size_t xt = (big + (size_t)h * (c->stride + 32)) * 2;
+  const size_t xt = (big * 2 + (size_t)h * (c->stride + 32)) * 2;   // (x2: widths below 64 are padded to 64 columns)
   L.xt_hi = take(xt);
   L.xt_lo = take(xt);
   size_t wp = 0;
   if (mbd_tc_enabled())
     mbd_for_each_conv(c, [&](int, int cin, int cout, int k, int) {
-      if (mbd_tc_eligible(cin)) wp += ((size_t)k * cout * cin * 2 + 255) / 256 * 256;
+      if (mbd_tc_eligible(cin)) wp += ((size_t)k * cout * mbd_tc_cpad(cin) * 2 + 255) / 256 * 256;
     });
   L.wpack = take(wp * c->n_models + 256);
   L.total = o;
@@ -479,13 +508,14 @@ extern "C" int mvb_mbd_create(const mvb_mbd_config* cfg, const void* d_arena, si
         if (!ok || !mbd_tc_eligible(cin)) return;
         const int gi = m * h->per_model + ti;
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(h->ws + L.wpack + wo);
-        k_mbd_pack_w<<<148 * 4, 256>>>(h->w(gi), cout, cin, k, tr, dst);
+        const int cp = mbd_tc_cpad(cin);
+        k_mbd_pack_w<<<148 * 4, 256>>>(h->w(gi), cout, cin, cp, k, tr, dst);
         mvb_mbd::TcW w{};
         w.Cin = cin; w.Cout = cout; w.K = k;
-        ok = ok && make_tmap_bf16_3d(&w.tmA, dst, (uint64_t)cin, (uint64_t)cout, (uint64_t)k, (uint64_t)cout * cin * 2, 128);
+        ok = ok && make_tmap_bf16_3d(&w.tmA, dst, (uint64_t)cp, (uint64_t)cout, (uint64_t)k, (uint64_t)cout * cp * 2, 128);
         h->tc_of[gi] = (int)h->tcw.size();
         h->tcw.push_back(w);
-        wo += ((size_t)k * cout * cin * 2 + 255) / 256 * 256;
+        wo += ((size_t)k * cout * cp * 2 + 255) / 256 * 256;
       });
     cudaError_t e = cudaDeviceSynchronize();
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_mbd_tc_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM);
@@ -515,7 +545,7 @@ static int gn_stats(mvb_mbd* h, cudaStream_t s, const float* x, int C, int T, in
   double* part = reinterpret_cast<double*>(h->ws + mbd_layout(&h->cfg).gn_part);
   const size_t n = (size_t)(C / groups) * T;
   k_gn_partial<<<dim3(groups, GN_SPLIT), 256, 0, s>>>(x, n, part);
-  k_gn_final<<<1, 64, 0, s>>>(part, groups, (double)n, 1e-5f, stats);
+  k_gn_final<<<groups, 32, 0, s>>>(part, groups, (double)n, 1e-5f, stats);
   MCK(cudaGetLastError());
   return MVB_OK;
 }
@@ -528,15 +558,16 @@ static int launch_conv_tc(mvb_mbd* h, cudaStream_t s, const ConvP& p, int widx, 
   __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(h->ws + L.xt_hi);
   __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(h->ws + L.xt_lo);
   const int Tpad = kind == 1 ? (p.Tin + stride - 1) / stride * stride : p.Tin;
-  k_mbd_prep_t<<<dim3((Tpad + 31) / 32, (p.Cin + 63) / 64), 256, 0, s>>>(p.x, p.Cin, p.Tin, Tpad, p.gn_stats, p.gn_w, p.gn_b,
-                                                                      p.gn_stats ? p.Cin / p.groups : 1, hi, lo);
+  const int Cp = mbd_tc_cpad(p.Cin);
+  k_mbd_prep_t<<<dim3((Tpad + 31) / 32, Cp / 64), 256, 0, s>>>(p.x, p.Cin, Cp, p.Tin, Tpad, p.gn_stats, p.gn_w, p.gn_b,
+                                                              p.gn_stats ? p.Cin / p.groups : 1, hi, lo);
   MCK(cudaGetLastError());
-  const uint64_t rows = kind == 1 ? Tpad / stride : p.Tin, cols = kind == 1 ? (uint64_t)stride * p.Cin : p.Cin;
+  const uint64_t rows = kind == 1 ? Tpad / stride : p.Tin, cols = kind == 1 ? (uint64_t)stride * Cp : Cp;
   CUtensorMap tBhi, tBlo;
   if (!make_tmap_bf16(&tBhi, hi, rows, cols, 128) || !make_tmap_bf16(&tBlo, lo, rows, cols, 128))
     return mvb::set_error(MVB_ERR_CUDA, "mbd: activation tensor map");
   TcConvP q{};
-  q.Cin = p.Cin; q.M = p.Cout; q.out = p.y; q.ldo = p.Tout; q.bias = p.bias; q.emb = p.emb; q.resid = p.resid;
+  q.Cin = Cp; q.M = p.Cout; q.out = p.y; q.ldo = p.Tout; q.bias = p.bias; q.emb = p.emb; q.resid = p.resid;
   q.Ncols = kind == 2 ? p.Tin : p.Tout;
   q.ostride = kind == 2 ? stride : 1;
   TcTaps& t = q.taps;
@@ -548,7 +579,7 @@ static int launch_conv_tc(mvb_mbd* h, cudaStream_t s, const ConvP& p, int widx, 
     for (int k = 0; k < K; ++k) {
       const int o = k - p.pad;
       const int qd = o >= 0 ? o / stride : -((-o + stride - 1) / stride);
-      t.a_z[0][k] = k; t.b_shift[0][k] = qd; t.b_col[0][k] = (o - qd * stride) * p.Cin;
+      t.a_z[0][k] = k; t.b_shift[0][k] = qd; t.b_col[0][k] = (o - qd * stride) * Cp;
     }
   } else {
     t.n_ph = stride; t.n_slots = 2;
@@ -666,11 +697,11 @@ static int unet_forward(mvb_mbd* h, cudaStream_t s, int m, int step, const float
 }
 
 static int split_lows(mvb_mbd* h, cudaStream_t s, const float* x, int T, int n_bands, const float* bank, int L, float* low) {
-  const size_t smem = (size_t)(256 + 2 * L) * 4;
+  const size_t smem = (size_t)(FIR_TT + 3 * L) * 4;
   static PerDeviceOnce attr;
   if (attr.pending()) { MCK(cudaFuncSetAttribute(k_fir_bank, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr.mark(); }
   if (smem > 64 * 1024) return mvb::set_error(MVB_ERR_UNSUPPORTED, "mbd: filter length %d", L);
-  k_fir_bank<<<dim3((T + 255) / 256, n_bands - 1), 256, smem, s>>>(x, T, bank, L, low);
+  k_fir_bank<<<dim3((T + FIR_TT - 1) / FIR_TT, (n_bands - 1 + 1) / 2), 256, smem, s>>>(x, T, bank, L, n_bands - 1, low);
   MCK(cudaGetLastError());
   (void)h;
   return MVB_OK;

@@ -8,7 +8,8 @@
 // s output phases with two taps each.  One CTA = 128 output channels x 128 time columns: A tiles (weights, 16 KB) and the
 // two B tiles (hi, lo: 128 rows each, together the N = 256 UMMA operand) arrive by TMA into a 4-stage ring, one elected
 // thread issues 4 x tcgen05.mma (128 x 256 x 16) per 64-channel block, the fp32 accumulator lives in 256 TMEM columns and
-// four epilogue warps add hi + lo + bias (+ residual) and store channel-major.
+// four epilogue warps add hi + lo + bias, transpose 32 x 32 blocks through shared memory and add the residual / store
+// channel-major rows with the lanes along time (coalesced).
 //
 // Numerics: weights are rounded to bf16 (the reference's own convolutions run in TF32 under torch's cuDNN default
 // `allow_tf32=True`, 10-bit mantissa on BOTH operands); activations are exact to 2^-17; accumulation is fp32.
@@ -33,7 +34,7 @@ struct TcConvP {
 
 constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = 128 * 64 * 2, TC_B_BYTES = 256 * 64 * 2, TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr size_t TC_SMEM = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 1) * 8 + 64;
+constexpr size_t TC_SMEM = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (2 * TC_STAGES + 1) * 8 + 64 + 4 * 32 * 33 * 4;   // + epilogue transpose tiles
 
 __device__ __forceinline__ void tc_tma3(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -113,29 +114,47 @@ k_mbd_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (ptx::elect_one()) ptx::umma_commit(ptx::smem_u32(bars + 2 * S));
     __syncwarp();
   } else if (warp >= 4) {
+    // Epilogue: each warp owns 32 accumulator lanes (output channels).  A 32 x 32 block goes TMEM -> registers (lane = channel)
+    // -> a padded smem tile -> global with lane = TIME, so that the residual reads and the stores are contiguous 128-byte rows
+    // instead of 32 scattered sectors per instruction (the channel-major activations have stride ldo between channels).
     const int w4 = warp - 4;
-    const int co = cot * 128 + 32 * w4 + lane;
+    const int co_w = cot * 128 + 32 * w4;               // first channel of this warp
     const uint32_t tbase = tmem_base + ((uint32_t)(32 * w4) << 16);
-    const bool row_ok = co < p.M;
-    float add = 0.f;
-    if (row_ok) add = (p.bias ? p.bias[co] : 0.f) + (p.emb ? p.emb[co] : 0.f);
-    const size_t obase = (size_t)(row_ok ? co : 0) * p.ldo + ph;
+    float* tp = reinterpret_cast<float*>(tmem_slot + 4) + w4 * (32 * 33);
     ptx::mbar_wait(ptx::smem_u32(bars + 2 * S), 0);
     ptx::tc_fence_after();
-    for (int c0 = 0; c0 < 128; c0 += 16) {
-      uint32_t hi[16], lo[16];
-      ptx::tmem_ld16(tbase + c0, hi);
-      ptx::tmem_ld16(tbase + 128 + c0, lo);
-      ptx::tmem_ld_wait();
+    if (co_w < p.M) {
+      const int co = co_w + lane;
+      float add = 0.f;
+      if (co < p.M) add = (p.bias ? p.bias[co] : 0.f) + (p.emb ? p.emb[co] : 0.f);
+      const int rows = min(32, p.M - co_w);
+      for (int c0 = 0; c0 < 128 && t0 + c0 < p.Ncols; c0 += 32) {
+        uint32_t hi[32], lo[32];
+        ptx::tmem_ld16(tbase + c0, *reinterpret_cast<uint32_t(*)[16]>(hi));
+        ptx::tmem_ld16(tbase + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(hi + 16));
+        ptx::tmem_ld16(tbase + 128 + c0, *reinterpret_cast<uint32_t(*)[16]>(lo));
+        ptx::tmem_ld16(tbase + 128 + c0 + 16, *reinterpret_cast<uint32_t(*)[16]>(lo + 16));
+        ptx::tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int n = t0 + c0 + i;
-        if (row_ok && n < p.Ncols) {
-          const size_t idx = obase + (size_t)n * p.ostride;
-          float v = __uint_as_float(hi[i]) + __uint_as_float(lo[i]) + add;
-          if (p.resid) v += p.resid[idx];
-          p.out[idx] = v;
+        for (int i = 0; i < 32; ++i) tp[lane * 33 + i] = __uint_as_float(hi[i]) + __uint_as_float(lo[i]) + add;
+        __syncwarp();
+        const int n = t0 + c0 + lane;
+        if (n < p.Ncols) {
+          const size_t col = (size_t)n * p.ostride + ph;
+          // residual reads in batches of 8 rows: issued back to back, not one dependent load -> store pair per row
+          for (int r0 = 0; r0 < rows; r0 += 8) {
+            float rv[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int r = min(r0 + j, rows - 1);
+              rv[j] = p.resid ? __ldg(p.resid + (size_t)(co_w + r) * p.ldo + col) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (r0 + j < rows) p.out[(size_t)(co_w + r0 + j) * p.ldo + col] = tp[(r0 + j) * 33 + lane] + rv[j];
+          }
         }
+        __syncwarp();
       }
     }
     ptx::tc_fence_before();
@@ -149,7 +168,7 @@ k_mbd_tc_conv(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
 // Time-major two-term bf16 copy of a layer input: hi/lo[t][c] = split(f(x[c][t])), f = relu(GroupNorm) when stats != null;
 // rows T .. Tpad-1 are written as zero (right padding of the strided convolution).  Tile: 64 channels x 32 samples.
-static __global__ void __launch_bounds__(256) k_mbd_prep_t(const float* __restrict__ x, int C, int T, int Tpad, const float* __restrict__ stats,
+static __global__ void __launch_bounds__(256) k_mbd_prep_t(const float* __restrict__ x, int C, int Cp, int T, int Tpad, const float* __restrict__ stats,
                                                            const float* __restrict__ gw, const float* __restrict__ gb, int cpg,
                                                            __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   __shared__ float tile[64][33];
@@ -172,26 +191,27 @@ static __global__ void __launch_bounds__(256) k_mbd_prep_t(const float* __restri
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int tl = ty * 4 + i, t = t0 + tl, c = c0 + 2 * tx;
-    if (t < Tpad && c < C) {
+    if (t < Tpad && c < Cp) {       // columns C .. Cp-1 (channel padding to a multiple of 64) are written as zero
       const float a = tile[2 * tx][tl], b = tile[2 * tx + 1][tl];
       const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
       __nv_bfloat162 h2, l2;
       h2.x = ah; h2.y = bh;
       l2.x = __float2bfloat16_rn(a - __bfloat162float(ah));
       l2.y = __float2bfloat16_rn(b - __bfloat162float(bh));
-      *reinterpret_cast<__nv_bfloat162*>(hi + (size_t)t * C + c) = h2;
-      *reinterpret_cast<__nv_bfloat162*>(lo + (size_t)t * C + c) = l2;
+      *reinterpret_cast<__nv_bfloat162*>(hi + (size_t)t * Cp + c) = h2;
+      *reinterpret_cast<__nv_bfloat162*>(lo + (size_t)t * Cp + c) = l2;
     }
   }
 }
 
-// Weight repack to bf16 [tap][Cout][Cin]: transposed = 0: w is Conv1d [Cout][Cin][K]; 1: ConvTranspose1d [Cin][Cout][K].
-static __global__ void k_mbd_pack_w(const float* __restrict__ w, int Cout, int Cin, int K, int transposed, __nv_bfloat16* __restrict__ out) {
-  const size_t n = (size_t)K * Cout * Cin;
+// Weight repack to bf16 [tap][Cout][Cp]: transposed = 0: w is Conv1d [Cout][Cin][K]; 1: ConvTranspose1d [Cin][Cout][K].
+// (Cp = Cin rounded up to a multiple of 64; the padding columns are zero.)
+static __global__ void k_mbd_pack_w(const float* __restrict__ w, int Cout, int Cin, int Cp, int K, int transposed, __nv_bfloat16* __restrict__ out) {
+  const size_t n = (size_t)K * Cout * Cp;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int ci = (int)(i % Cin), co = (int)((i / Cin) % Cout), k = (int)(i / ((size_t)Cin * Cout));
+    const int ci = (int)(i % Cp), co = (int)((i / Cp) % Cout), k = (int)(i / ((size_t)Cp * Cout));
     const size_t src = transposed ? ((size_t)ci * Cout + co) * K + k : ((size_t)co * Cin + ci) * K + k;
-    out[i] = __float2bfloat16_rn(w[src]);
+    out[i] = __float2bfloat16_rn(ci < Cin ? w[src] : 0.f);
   }
 }
 

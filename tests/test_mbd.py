@@ -35,7 +35,8 @@ def test_restatement_invariants():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("frames", [12, 40])
-def test_mbd_device_vs_restatement(frames):
+def test_mbd_device_vs_restatement(frames, monkeypatch):
+    monkeypatch.setenv("MVB_MBD_NO_TC", "1")        # the fp32 CUDA-core kernels (the tensor-core lowering has its own test below)
     from mvb200.mbd import MBDSettings, MultiBandDiffusionEngine, ScheduleSettings, UnetSettings
     ck = synth.mbd_checkpoint(SMALL, 0)
     settings = MBDSettings(n_models=2, unet=UnetSettings(hidden=16, depth=2, growth=2.0, kernel=8, stride=4, res_blocks=1, norm_groups=4),
@@ -65,14 +66,15 @@ def _round_conv_weights_to_bf16(ck):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kernel,stride,frames", [(8, 4, 12), (8, 4, 33), (4, 2, 12)])
-def test_mbd_tensor_core_convs_vs_restatement(kernel, stride, frames):
-    """Channel widths that are multiples of 64 take the tcgen05 path (csrc/mbd_tc.cuh): shifted-GEMM Conv1d (dilation 1
+@pytest.mark.parametrize("kernel,stride,frames,hidden", [(8, 4, 12, 64), (8, 4, 33, 64), (4, 2, 12, 64), (8, 4, 12, 48)])
+def test_mbd_tensor_core_convs_vs_restatement(kernel, stride, frames, hidden, monkeypatch):
+    """Input widths >= 32 channels take the tcgen05 path (csrc/mbd_tc.cuh): shifted-GEMM Conv1d (dilation 1
     and 2), the strided encoder convolution and the phase-decomposed ConvTranspose1d.  With conv weights representable in
     bf16 the path is exact to fp32 round-off against the fp32 restatement; with arbitrary fp32 weights the only deviation
     is the bf16 rounding of the taps (reported, bounded)."""
+    monkeypatch.delenv("MVB_MBD_NO_TC", raising=False)
     from mvb200.mbd import MBDSettings, MultiBandDiffusionEngine, ScheduleSettings, UnetSettings
-    ucfg = dict(hidden=64, depth=2, growth=2.0, kernel=kernel, stride=stride, res_blocks=2, norm_groups=4)
+    ucfg = dict(hidden=hidden, depth=2, growth=2.0, kernel=kernel, stride=stride, res_blocks=2, norm_groups=4)
     cfg = M.MBDConfig(n_models=2, unet=M.UnetCfg(**ucfg), proc_bands=4, eq_bands=8, step_list=[999, 666, 333, 0])
     settings = MBDSettings(n_models=2, unet=UnetSettings(**ucfg), schedule=ScheduleSettings(), proc_bands=4, eq_bands=8,
                            step_list=[999, 666, 333, 0])
