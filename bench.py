@@ -444,7 +444,7 @@ def pipeline_leg(model, prompts, spk, h_spk_pinned, utts, steps, device, world, 
                             "audio_post_pcm16": round(post_s / steps * 1e3, 2)},
             "mbd_config": f"PARAMETRISED, parity unpinned: {mbd_cfg.n_models} band UNets (hidden {u.hidden}, depth {u.depth}, growth {u.growth}, "
                           f"k{u.kernel}/s{u.stride}, {u.res_blocks} res block) x {len(mbd_cfg.steps()) - 1} calls, {mbd_cfg.eq_bands}-band re-EQ; "
-                          "convolutions with >= 64 input channels on tcgen05 (bf16 taps, hi/lo activations), the rest fp32 CUDA-core",
+                          "convolutions with >= 32 input channels on tcgen05 (bf16 taps, two-term bf16 activations, fp32 accumulate), the 1-channel input conv and the 1x1 condition conv on fp32 CUDA cores",
             "stage_rooflines": stage_rooflines,
             "coverage": "stage-1 (750 tokens) + token adapters + stage-2 (6 codebooks) + EnCodec SEANet decoder + multi-band diffusion "
                         "+ loudness/compressor/PCM16 on device, wav bytes on the host; DeepFilterNet is NOT implemented"}

@@ -178,17 +178,22 @@ struct mvb_s1 {
 };
 
 
-// Static decomposition of one matrix over `ctas` CTAs: the K split that minimises the busiest CTA's k-blocks.
-static PcMat plan_pc(int M, int K, int ctas, int tile_rows) {
+// Static decomposition of one matrix over `ctas` CTAs: the K split that minimises the busiest CTA's modelled phase time.
+static PcMat plan_pc(int M, int K, int ctas, int tile_rows, int force_S = 0) {
   PcMat best{};
   long best_cost = -1;
   const int T = (M + tile_rows - 1) / tile_rows, KB = K / 64;
   for (int S = 1; S <= KB && S <= 32 && S <= ctas; ++S) {
+    if (force_S > 0 && S != force_S) continue;   // MVB_PC_SPLITS experiment switch
     const int Gp = ctas / S;
     const int tiles_per = (T + Gp - 1) / Gp;
     const int kb_per = (KB + S - 1) / S;
     if (kb_per > PC_BKB_MAX) continue;
-    const long cost = (long)tiles_per * kb_per;
+    // Cost of a phase in tile-load units (fitted on B200, profiles/r2_step_time_ksplit_sweep.jsonl): every tile a CTA owns
+    // costs its k-blocks plus ~2.5 for the accumulator drain (tcgen05.ld + red.add), and staging the activation operand
+    // costs ~2 per k-block of the CTA's K slice (one dependent L2 round trip per 256 chunks).  The round-1 cost
+    // (tiles x k-blocks only) chose 3 / 8 / 8 / 9 splits for qkv / wo / w1|w3 / w2; this one chooses 8 / 16 / 8 / 22.
+    const long cost = (long)tiles_per * (2 * kb_per + 5) + 4 * kb_per;
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
       best.T = T; best.KB = KB; best.S = S; best.G = Gp;
@@ -317,11 +322,13 @@ extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size
       okv = okv && make_tmap_bf16_3d(&h->tm3[wbv][3], h->lw(0, 5), D, F, NL, stride, rows);
       okv = okv && make_tmap_bf16_3d(&h->tm3[wbv][4], h->lw(0, 6), F, D, NL, stride, rows);
       okv = okv && make_tmap_bf16_3d(&h->tm3[wbv][5], h->w(4), D, V, 1, (uint64_t)V * D * 2, rows);
-      h->pm[wbv][0] = plan_pc(3 * D, D, h->n_sm, rows);
-      h->pm[wbv][1] = plan_pc(D, D, h->n_sm, rows);
-      h->pm[wbv][2] = plan_pc(2 * F, D, h->n_sm, rows);
-      h->pm[wbv][3] = plan_pc(D, F, h->n_sm, rows);
-      h->pm[wbv][4] = plan_pc(V, D, h->n_sm, rows);
+      int fs[5] = {0, 0, 0, 0, 0};               // MVB_PC_SPLITS="q_o_w13_w2_head": force the K split of a matrix (0 = planner)
+      if (const char* e = getenv("MVB_PC_SPLITS")) sscanf(e, "%d_%d_%d_%d_%d", &fs[0], &fs[1], &fs[2], &fs[3], &fs[4]);
+      h->pm[wbv][0] = plan_pc(3 * D, D, h->n_sm, rows, fs[0]);
+      h->pm[wbv][1] = plan_pc(D, D, h->n_sm, rows, fs[1]);
+      h->pm[wbv][2] = plan_pc(2 * F, D, h->n_sm, rows, fs[2]);
+      h->pm[wbv][3] = plan_pc(D, F, h->n_sm, rows, fs[3]);
+      h->pm[wbv][4] = plan_pc(V, D, h->n_sm, rows, fs[4]);
       for (int i = 0; i < 5; ++i) okv = okv && h->pm[wbv][i].S > 0;
       okv = okv && (F % rows == 0) && (D % rows == 0);     // w1 | w3 share one tile index space: F must be whole tiles
       h->pc_ok2[wbv] = okv;
