@@ -73,7 +73,8 @@ size_t mvb_s1_workspace_bytes(const mvb_s1_config* cfg);
 
 /* Build an engine over caller-owned device memory.  `offsets` is a HOST array of
  * MVB_S1_GLOBAL_TENSORS + n_layer*MVB_S1_LAYER_TENSORS byte offsets into d_arena.  d_workspace must
- * be zero-filled.  Replaces build_model()/Transformer.__init__/setup_caches/setup_spk_cond_mask
+ * be zero-filled; with a bf16 cache the call zero-fills d_kv itself (the attention kernel reads whole 64-position tiles,
+ * so positions that were never written must hold finite values).  Replaces build_model()/Transformer.__init__/setup_caches/setup_spk_cond_mask
  * (fast_inference_utils.py:324-352, fast_model.py:116-148); there is no JIT/compile step. */
 int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size_t arena_bytes,
                   const uint64_t* offsets, void* d_kv, void* d_workspace, mvb_s1** out);

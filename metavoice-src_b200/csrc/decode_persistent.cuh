@@ -132,6 +132,8 @@ struct PcParams {
   char* kv;
   size_t kv_half;  // bytes of one layer's K (or V) region
   unsigned* bar;   // grid-wide arrival counter (zero at launch)
+  int att_mma;       // 1: bf16 KV tiles arrive 128B-swizzled through tm_kv and the attention runs on mma.sync (see the attention phase)
+  long long kv_rows_half;   // cache rows (positions) of one layer's K (or V) region = kv_half / 256
   long long* trace;  // optional [gridDim][PC_TRACE_EVENTS] clock64 stamps of compute-thread 0 (debug)
   S1State st;
 };
@@ -292,6 +294,31 @@ __device__ __forceinline__ float fast_exp(float x) {
   return y;
 }
 
+// order-preserving float <-> int32 image (for redux.sync.max on floats); -inf maps below every finite value
+__device__ __forceinline__ int float_to_ordered(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// D[16x8] += A[16x16] * B[16x8], bf16 operands, fp32 accumulate (fragment layouts: PTX ISA, mma.m16n8k16)
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (x0, x1) -> packed bf16 pair of the high terms and of the residuals (x = hi + lo to 2^-17)
+__device__ __forceinline__ void pack_hi_lo(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+  const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+  hi = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  lo = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+}
+
 template <bool KV_FP32>
 __device__ __forceinline__ void load8s(const uint8_t* tile, int p, int sub, float (&v)[8]) {
   if (KV_FP32) {
@@ -310,7 +337,7 @@ __global__ void __launch_bounds__(PC_THREADS, 1)
 k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_o,
                     const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w3,
                     const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_head,
-                    const PcParams p) {
+                    const __grid_constant__ CUtensorMap tm_kv, const PcParams p) {
   using Cfg = PcCfg<NB, WB>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int RH = Cfg::RH;
@@ -465,12 +492,24 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           ++kv_ctr;
           ptx::mbar_wait(ptx::smem_u32(sh.kv_empty + ks), ph ^ 1u);
           if (ptx::elect_one()) {
-            const uint32_t bytes = (uint32_t)npos * 128 * esz;
             const uint32_t full = ptx::smem_u32(sh.kv_full + ks);
-            ptx::mbar_arrive_expect_tx(full, 2 * bytes);
             uint8_t* dst = kvbuf + (size_t)ks * 2 * PC_KV_TILE_BYTES;
-            bulk_load(ptx::smem_u32(dst), kbase + e.off, bytes, full);
-            bulk_load(ptx::smem_u32(dst + PC_KV_TILE_BYTES), vbase + e.off, bytes, full);
+            if (!KV_FP32 && p.att_mma) {
+              // 64 positions x 128 dims as two 128B-swizzled [64 x 64] boxes per operand (conflict-free ldmatrix); rows past
+              // npos are older / zero cache contents and are masked by the consumer
+              const int row = (int)((long long)l * 2 * p.kv_rows_half + (long long)(e.off >> 8));
+              const int rowv = row + (int)p.kv_rows_half;
+              ptx::mbar_arrive_expect_tx(full, 2u * PC_KV_TILE_BYTES);
+              ptx::tma_load_2d(ptx::smem_u32(dst), &tm_kv, full, 0, row);
+              ptx::tma_load_2d(ptx::smem_u32(dst + 8192), &tm_kv, full, 64, row);
+              ptx::tma_load_2d(ptx::smem_u32(dst + PC_KV_TILE_BYTES), &tm_kv, full, 0, rowv);
+              ptx::tma_load_2d(ptx::smem_u32(dst + PC_KV_TILE_BYTES + 8192), &tm_kv, full, 64, rowv);
+            } else {
+              const uint32_t bytes = (uint32_t)npos * 128 * esz;
+              ptx::mbar_arrive_expect_tx(full, 2 * bytes);
+              bulk_load(ptx::smem_u32(dst), kbase + e.off, bytes, full);
+              bulk_load(ptx::smem_u32(dst + PC_KV_TILE_BYTES), vbase + e.off, bytes, full);
+            }
           }
           __syncwarp();
         }
@@ -909,6 +948,190 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
         zero_slice(p.gu, (size_t)PC_RPAD * 2 * p.F);   // free since the previous layer's w2 phase; ordered by the next arrive
         grid_wait();
         stamp();
+        if (!KV_FP32 && p.att_mma) {
+          // ===== tensor-core attention (bf16 cache): per 64-position tile  S = K q  and  o += V^T p  as mma.sync m16n8k16 with the
+          // vector operand in column 0 of the 8-wide B fragment (lanes 0..3), K / V^T blocks through ldmatrix from the
+          // 128B-swizzled tiles.  q and p ride as two bf16 terms (hi + lo, 2^-17), K and V are exactly the cache contents,
+          // accumulation is fp32: the same numerics class as the scalar path.  Warp w scores positions [16w, 16w+16) and
+          // accumulates output dims [32w, 32w+32); every warp keeps the identical running (max, sum).
+          char* kbase = p.kv + (size_t)l * 2 * p.kv_half;
+          char* vbase = kbase + p.kv_half;
+          uint32_t* q_hi = reinterpret_cast<uint32_t*>(sh.o);     // [64] packed pairs   (sh.o is the scalar path's merge buffer)
+          uint32_t* q_lo = q_hi + 64;                             // [64]
+          float* scv = reinterpret_cast<float*>(q_lo + 64);       // [64] scores of the tile
+          float* qf = scv + 64;                                   // [128] fp32 q (current-token dot product)
+          uint32_t* pw = reinterpret_cast<uint32_t*>(qf + 128) + cw * 64;   // per warp: [32] hi pairs | [32] lo pairs
+          const int g = lane >> 2, t4 = lane & 3, mat = lane >> 3;
+          float m = -INFINITY, lsum = 0.f, kcur = 0.f, vcur = 0.f;
+          float oacc[2][4];
+          const int n_tiles = sh.n_att_tiles;
+#ifdef PC_ATT_PROF
+          long long a_t[5] = {0, 0, 0, 0, 0}, a_c = clock64();   // begin | append cur | kv wait | tile math | cur + unit end
+#define PC_ATT_MARK(k) { const long long _n = clock64(); a_t[k] += _n - a_c; a_c = _n; }
+#else
+#define PC_ATT_MARK(k)
+#endif
+          for (int ti = 0; ti < n_tiles; ++ti) {
+            const AttTile e = sh.att_tab[ti];
+            const int npos = (int)(e.meta & 0xffu);
+            const bool has_cur = e.meta & 0x100u, unit_first = e.meta & 0x200u, unit_last = e.meta & 0x400u,
+                       owns_cur = e.meta & 0x800u;
+            const int r = e.where & 0xff, h = (e.where >> 8) & 0xff, z = (e.where >> 16) & 0xff, cr = e.where >> 24;
+            const int L = e.L;
+            if (unit_first) {
+              const float* qrow = p.qkv + (size_t)r * 3 * p.D + h * 128;
+              const float qraw = __ldcg(qrow + ct);
+              const float ssr = __ldcg(stat_a + r);
+              if (owns_cur) {
+                kcur = __ldcg(qrow + p.D + ct);
+                vcur = __ldcg(qrow + 2 * p.D + ct);
+              }
+              const float rsn = rsqrtf(ssr * inv_D + p.eps);      // RMSNorm scale of this row (fast_model.py:254-255)
+              const float qv = qraw * (0.08838834764831845f * rsn);
+              kcur *= rsn;
+              vcur *= rsn;
+              const float qn = __shfl_down_sync(0xffffffffu, qv, 1);
+              qf[ct] = qv;
+              if ((ct & 1) == 0) pack_hi_lo(qv, qn, q_hi[ct >> 1], q_lo[ct >> 1]);
+              m = -INFINITY; lsum = 0.f;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { oacc[0][i] = 0.f; oacc[1][i] = 0.f; }
+              compute_sync();                                    // q visible to every warp
+            }
+            PC_ATT_MARK(0)
+            if (has_cur) {
+              // append the new token's k, v to the cache, rounded as the cache stores them; share them via smem
+              const size_t ce = (((size_t)cr * p.H + h) * p.S_max + (L - 1)) * 128 + ct;
+              const __nv_bfloat16 kb16 = __float2bfloat16_rn(kcur), vb16 = __float2bfloat16_rn(vcur);
+              reinterpret_cast<__nv_bfloat16*>(kbase)[ce] = kb16;
+              reinterpret_cast<__nv_bfloat16*>(vbase)[ce] = vb16;
+              kcur = __bfloat162float(kb16);
+              vcur = __bfloat162float(vb16);
+              asm volatile("fence.proxy.async.global;" ::: "memory");   // later tokens fetch this row with TMA (async proxy)
+              sh.cur[ct] = kcur;
+              sh.cur[128 + ct] = vcur;
+            }
+            PC_ATT_MARK(1)
+            if (npos > 0) {
+              const uint32_t ks = kv_ctr % Cfg::NKV, ph = (kv_ctr / Cfg::NKV) & 1u;
+              ++kv_ctr;
+              ptx::mbar_wait(ptx::smem_u32(sh.kv_full + ks), ph);
+              PC_ATT_MARK(2)
+              const uint32_t kt = ptx::smem_u32(kvbuf + (size_t)ks * 2 * PC_KV_TILE_BYTES);
+              const uint32_t vt = kt + PC_KV_TILE_BYTES;
+              if (16 * cw < npos) {
+                // ---- scores of positions [16w, 16w+16): A = K rows, B = q (hi, lo) in column 0
+                // four independent accumulator chains (hi / lo terms x even / odd k-steps): the mma latency, not its issue
+                // rate, is what a single warp per scheduler pays
+                float c4[4][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { c4[i][0] = c4[i][1] = c4[i][2] = c4[i][3] = 0.f; }
+                const int rr = 16 * cw + (lane & 7) + ((mat & 1) << 3);
+#pragma unroll
+                for (int k8 = 0; k8 < 8; ++k8) {
+                  const int chunk = ((k8 & 3) << 1) + (mat >> 1);
+                  uint32_t a[4];
+                  ldsm_x4(kt + (uint32_t)((k8 >> 2) * 8192 + rr * 128 + ((chunk ^ (rr & 7)) << 4)), a);
+                  const uint32_t bh0 = lane < 4 ? q_hi[k8 * 8 + t4] : 0u, bh1 = lane < 4 ? q_hi[k8 * 8 + t4 + 4] : 0u;
+                  const uint32_t bl0 = lane < 4 ? q_lo[k8 * 8 + t4] : 0u, bl1 = lane < 4 ? q_lo[k8 * 8 + t4 + 4] : 0u;
+                  mma_bf16_16816(c4[(k8 & 1) * 2], a, bh0, bh1);
+                  mma_bf16_16816(c4[(k8 & 1) * 2 + 1], a, bl0, bl1);
+                }
+                if (t4 == 0) {
+                  const int p0 = 16 * cw + g;
+                  scv[p0] = p0 < npos ? (c4[0][0] + c4[2][0]) + (c4[1][0] + c4[3][0]) : -INFINITY;
+                  scv[p0 + 8] = p0 + 8 < npos ? (c4[0][2] + c4[2][2]) + (c4[1][2] + c4[3][2]) : -INFINITY;
+                }
+              } else if (lane < 16) {
+                scv[16 * cw + lane] = -INFINITY;
+              }
+              compute_sync();                                    // all 64 scores visible
+              // ---- online softmax over the tile (identical in every warp)
+              // tile max with ONE redux.sync on an order-preserving integer image of the floats (a 5-step shuffle butterfly
+              // is ~150 cycles of dependent latency); the running sum stays per lane and is reduced once per unit
+              const float s0 = scv[lane], s1 = scv[lane + 32];
+              const float mn = fmaxf(m, ordered_to_float(__reduce_max_sync(0xffffffffu, float_to_ordered(fmaxf(s0, s1)))));
+              const float mref = (mn == -INFINITY) ? 0.f : mn;
+              const float corr = fast_exp(m - mref), p0v = fast_exp(s0 - mref), p1v = fast_exp(s1 - mref);
+              lsum = lsum * corr + (p0v + p1v);
+              m = mn;
+              {
+                const float n0 = __shfl_down_sync(0xffffffffu, p0v, 1), n1 = __shfl_down_sync(0xffffffffu, p1v, 1);
+                if ((lane & 1) == 0) {
+                  pack_hi_lo(p0v, n0, pw[lane >> 1], pw[32 + (lane >> 1)]);
+                  pack_hi_lo(p1v, n1, pw[16 + (lane >> 1)], pw[48 + (lane >> 1)]);
+                }
+              }
+              __syncwarp();
+              // ---- o[32w .. 32w+32) = o * corr + V^T p : A = V^T blocks (ldmatrix.trans), B = p (hi, lo) in column 0
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { oacc[0][i] *= corr; oacc[1][i] *= corr; }
+              float olo[2][4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { olo[0][i] = 0.f; olo[1][i] = 0.f; }
+              const int n_k4 = (npos + 15) >> 4;
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                if (k4 < n_k4) {
+                  const uint32_t bh0 = lane < 4 ? pw[k4 * 8 + t4] : 0u, bh1 = lane < 4 ? pw[k4 * 8 + t4 + 4] : 0u;
+                  const uint32_t bl0 = lane < 4 ? pw[32 + k4 * 8 + t4] : 0u, bl1 = lane < 4 ? pw[32 + k4 * 8 + t4 + 4] : 0u;
+                  const int pos = 16 * k4 + (lane & 7) + ((mat >> 1) << 3);
+#pragma unroll
+                  for (int mb = 0; mb < 2; ++mb) {
+                    const int d0 = 32 * cw + 16 * mb;
+                    const int chunk = ((d0 & 63) >> 3) + (mat & 1);
+                    uint32_t a[4];
+                    ldsm_x4_t(vt + (uint32_t)((d0 >> 6) * 8192 + pos * 128 + ((chunk ^ (pos & 7)) << 4)), a);
+                    mma_bf16_16816(oacc[mb], a, bh0, bh1);
+                    mma_bf16_16816(olo[mb], a, bl0, bl1);
+                  }
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { oacc[0][i] += olo[0][i]; oacc[1][i] += olo[1][i]; }
+              PC_ATT_MARK(3)
+            }
+            if (npos > 0 || has_cur) compute_sync();   // KV tile fully consumed; sh.cur visible
+            if (npos > 0 && ct == 0) ptx::mbar_arrive(ptx::smem_u32(sh.kv_empty + ((kv_ctr - 1) % Cfg::NKV)));
+            if (has_cur) {
+              // the current token (its k, v never left the chip): every warp applies the same update to its dims
+              float sd = 0.f;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) sd = fmaf(qf[lane * 4 + i], sh.cur[lane * 4 + i], sd);
+              sd = warp_sum(sd);
+              const float mn = fmaxf(m, sd), corr = __expf(m - mn), pc = __expf(sd - mn);
+              lsum = lsum * corr + (lane == 0 ? pc : 0.f);           // (lsum is a per-lane partial sum)
+#pragma unroll
+              for (int mb = 0; mb < 2; ++mb) {
+                const int d = 32 * cw + 16 * mb + g;
+                oacc[mb][0] = oacc[mb][0] * corr + pc * sh.cur[128 + d];
+                oacc[mb][2] = oacc[mb][2] * corr + pc * sh.cur[128 + d + 8];
+              }
+              m = mn;
+            }
+            if (unit_last) {
+              // every warp holds the same (m, l); output dims live in the lanes with t4 == 0 (column 0 of the C fragments)
+              const size_t pidx = ((size_t)r * p.H + h) * PC_MAX_CHUNKS + z;
+              if (t4 == 0) {
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                  const int d = 32 * cw + 16 * mb + g;
+                  p.part_o[pidx * 128 + d] = oacc[mb][0];
+                  p.part_o[pidx * 128 + d + 8] = oacc[mb][2];
+                }
+              }
+              const float ltot = warp_sum(lsum);
+              if (ct == 0) { p.part_ml[pidx * 2] = m; p.part_ml[pidx * 2 + 1] = ltot; }
+              compute_sync();   // q / score scratch and sh.cur are reused by the next unit
+              PC_ATT_MARK(4)
+            }
+          }
+#ifdef PC_ATT_PROF
+          if (p.trace != nullptr && ct == 0)
+            for (int k = 0; k < 5; ++k) p.trace[(size_t)cta * PC_TRACE_EVENTS + 380 + l * 5 + k] = a_t[k];
+#endif
+#undef PC_ATT_MARK
+        } else
         {
           char* kbase = p.kv + (size_t)l * 2 * p.kv_half;
           char* vbase = kbase + p.kv_half;

@@ -161,6 +161,8 @@ struct mvb_s1 {
   bool wb = false;                                    // streamed weights as the N = 256 UMMA B operand (measured slower: off)
   bool fused = true;                                  // sample inside the persistent kernel (multi-token launches)
   int pf_mode = 1, pf_ahead = 8, epi_mode = 2, kv_pf = 0;
+  int att_mma = 1;                                    // bf16 cache: attention on mma.sync over TMA-swizzled KV tiles (MVB_PC_ATT_MMA=0: scalar)
+  CUtensorMap tm_kv;                                  // 2-D map over the whole bf16 KV arena: [rows = layer, k|v, cache row, head, pos][128]
   CUtensorMap tm3[2][6];                              // [WB] 3-D (k, row, layer) maps: wqkv, wo, w1, w3, w2, head
   PcMat pm[2][5];
   bool pc_ok2[2] = {false, false};
@@ -298,6 +300,23 @@ extern "C" int mvb_s1_create(const mvb_s1_config* cfg, const void* d_arena, size
   if (const char* e = getenv("MVB_PF_MODE")) h->pf_mode = atoi(e);
   if (const char* e = getenv("MVB_PC_EPI")) h->epi_mode = atoi(e);
   if (const char* e = getenv("MVB_PC_KVPF")) h->kv_pf = atoi(e);
+  if (const char* e = getenv("MVB_PC_ATT_MMA")) h->att_mma = atoi(e);
+  memset(&h->tm_kv, 0, sizeof(h->tm_kv));
+  if (cfg->kv_dtype != MVB_KV_BF16 || cfg->block_size % 64 || cfg->head_dim != 128) h->att_mma = 0;
+  if (h->att_mma) {
+    // the tensor-core attention reads whole 64-position boxes: positions past the valid ones must hold finite values
+    CK(cudaMemset(h->kv, 0, (size_t)cfg->n_layer * 2 * h->kv_half_bytes()));
+    EncodeTiledFn fn = encode_tiled_fn();
+    const uint64_t rows = (uint64_t)cfg->n_layer * 2 * (h->kv_half_bytes() / 256);
+    cuuint64_t dims[2] = {128, rows};
+    cuuint64_t strides[1] = {256};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    if (!fn || rows >= (1ull << 31) ||
+        fn(&h->tm_kv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->kv, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      h->att_mma = 0;
+  }
   if (const char* e = getenv("MVB_PC_WB")) h->wb = atoi(e) != 0;
   if (const char* e = getenv("MVB_PC_FUSED")) h->fused = atoi(e) != 0;
   h->h_topk.assign(cfg->max_utts, 0);
@@ -561,6 +580,7 @@ static int launch_persistent(mvb_s1* h, cudaStream_t s, int n_utts, int n_steps,
   p.samp_part = h->wsp<float>(h->L.c_samp_part);
   p.samp_best = h->wsp<unsigned long long>(h->L.c_samp_best);
   p.kv = h->kv; p.kv_half = h->kv_half_bytes();
+  p.att_mma = h->att_mma; p.kv_rows_half = (long long)(h->kv_half_bytes() / 256);
   p.bar = h->wsp<unsigned>(h->L.c_bar);
   p.trace = (h->trace && h->n_sm <= 160) ? h->wsp<long long>(h->L.c_trace) : nullptr;
   p.st = h->st;
@@ -573,7 +593,7 @@ static int launch_persistent(mvb_s1* h, cudaStream_t s, int n_utts, int n_steps,
   const CUtensorMap* tm = h->tm3[wbv];
 #define MVB_PC_LAUNCH(FP, NBV, WBV)                                                                                   \
   CK(launch_pdl(h->pdl, k_decode_persistent<FP, NBV, WBV>, dim3(h->n_sm), dim3(PC_THREADS), PcCfg<NBV, WBV>::SMEM, s, \
-                tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], p))
+                tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], h->tm_kv, p))
   if (wbv) {
     if (fp && wide) MVB_PC_LAUNCH(true, 32, true);
     else if (fp) MVB_PC_LAUNCH(true, 16, true);

@@ -30,7 +30,7 @@ for item in spec.split(","):
     parts = item.split(":")
     kind, n = parts[0], int(parts[1])
     extra = dict(kv.split("=") for kv in parts[2].split("+")) if len(parts) > 2 and parts[2] else {}
-    for k in ("MVB_PC_WB", "MVB_PC_FUSED", "MVB_PF_MODE", "MVB_PF_AHEAD", "MVB_PC_EPI", "MVB_PC_KVPF", "MVB_PC_SPLITS"):
+    for k in ("MVB_PC_WB", "MVB_PC_FUSED", "MVB_PF_MODE", "MVB_PF_AHEAD", "MVB_PC_EPI", "MVB_PC_KVPF", "MVB_PC_SPLITS", "MVB_PC_ATT_MMA"):
         os.environ.pop(k, None)
     os.environ.update(extra)
     os.environ["MVB_PDL"] = "0" if kind.endswith("0") else "1"
