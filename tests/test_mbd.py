@@ -93,3 +93,23 @@ def test_mbd_tensor_core_convs_vs_restatement(kernel, stride, frames, hidden, mo
         err = float((got - want).abs().max() / want.abs().max())
         print(f"MBD tensor-core (k={kernel}, s={stride}, {T} samples, bf16-representable taps={exact}): rel err {err:.2e}")
         assert err < (2e-3 if exact else 3e-2)
+
+
+def test_flop_accounting_matches_the_restatement_shapes():
+    """bench.py's MBD roofline uses MultiBandDiffusionEngine.flops(): check it against a direct count over the restatement's
+    own layer shapes for the default parametrised configuration (187 GFLOP per UNet pass, 80 passes per utterance)."""
+    import types
+    from mvb200.mbd import MBDSettings, MultiBandDiffusionEngine
+    s = MBDSettings()
+    got = MultiBandDiffusionEngine.flops(types.SimpleNamespace(s=s), 120000, 375)
+    u, ch = s.unet, s.unet.channels()
+    t, cin, per = 120000, u.chin, 0.0
+    for c in ch:
+        t = -(-t // u.stride)
+        per += 2.0 * t * (u.kernel * cin * c)                    # Conv1d(cin, c, k, stride)
+        per += 2 * u.res_blocks * 2 * 2.0 * t * (3 * c * c)      # encoder + decoder ResBlocks
+        per += 2.0 * t * (u.kernel * c * cin)                    # ConvTranspose1d(c, cin, k, stride): every input sample x every tap
+        cin = c
+    per += 2.0 * 375 * u.codec_dim * ch[-1]
+    want = per * s.n_models * (len(s.steps()) - 1)
+    assert abs(got - want) / want < 1e-12 and 14.5e12 < got < 15.5e12
