@@ -965,23 +965,6 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           float m = -INFINITY, lsum = 0.f, kcur = 0.f, vcur = 0.f;
           float oacc[2][4];
           const int n_tiles = sh.n_att_tiles;
-          // the q / k / v rows of this CTA's SECOND unit (8-utterance batches: two (row, head) units per CTA) are requested now,
-          // so their L2 round trip overlaps the first unit instead of standing in front of the second
-          int ti2 = -1;
-          float pre_q = 0.f, pre_ss = 0.f, pre_k = 0.f, pre_v = 0.f;
-          for (int ti = 1; ti < n_tiles; ++ti)
-            if (sh.att_tab[ti].meta & 0x200u) { ti2 = ti; break; }
-          if (ti2 > 0) {
-            const AttTile e2 = sh.att_tab[ti2];
-            const int r2 = e2.where & 0xff, h2 = (e2.where >> 8) & 0xff;
-            const float* qrow2 = p.qkv + (size_t)r2 * 3 * p.D + h2 * 128;
-            pre_q = __ldcg(qrow2 + ct);
-            pre_ss = __ldcg(stat_a + r2);
-            if (e2.meta & 0x800u) {
-              pre_k = __ldcg(qrow2 + p.D + ct);
-              pre_v = __ldcg(qrow2 + 2 * p.D + ct);
-            }
-          }
 #ifdef PC_ATT_PROF
           long long a_t[5] = {0, 0, 0, 0, 0}, a_c = clock64();   // begin | append cur | kv wait | tile math | cur + unit end
 #define PC_ATT_MARK(k) { const long long _n = clock64(); a_t[k] += _n - a_c; a_c = _n; }
@@ -997,16 +980,11 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             const int L = e.L;
             if (unit_first) {
               const float* qrow = p.qkv + (size_t)r * 3 * p.D + h * 128;
-              float qraw, ssr;
-              if (ti == ti2) {
-                qraw = pre_q; ssr = pre_ss; kcur = pre_k; vcur = pre_v;
-              } else {
-                qraw = __ldcg(qrow + ct);
-                ssr = __ldcg(stat_a + r);
-                if (owns_cur) {
-                  kcur = __ldcg(qrow + p.D + ct);
-                  vcur = __ldcg(qrow + 2 * p.D + ct);
-                }
+              const float qraw = __ldcg(qrow + ct);
+              const float ssr = __ldcg(stat_a + r);
+              if (owns_cur) {
+                kcur = __ldcg(qrow + p.D + ct);
+                vcur = __ldcg(qrow + 2 * p.D + ct);
               }
               const float rsn = rsqrtf(ssr * inv_D + p.eps);      // RMSNorm scale of this row (fast_model.py:254-255)
               const float qv = qraw * (0.08838834764831845f * rsn);
