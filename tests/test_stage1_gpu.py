@@ -355,10 +355,13 @@ def test_full_generate_reproduces_reference_tokens(golden_dir, full_sd):
 
 
 # ---- the configuration bench.py times: 1.2 B model, bf16 KV cache, persistent fused kernel ------------------------------
-def test_persistent_kernel_logits_full_bf16_kv_vs_reference_golden(golden_dir, full_arena):
+@pytest.mark.parametrize("attention", ["mma", "scalar"])
+def test_persistent_kernel_logits_full_bf16_kv_vs_reference_golden(golden_dir, full_arena, attention, monkeypatch):
     """k_decode_persistent<bf16 KV, 16 columns> -- the exact kernel instance BENCH times -- at full size, prefill T=48
     then teacher-forced positions through mvb_s1_step_logits, against the reference's fp32 logits.  A bf16 cache
-    cannot meet 1e-3: the bound is the reference's OWN bf16-vs-fp32 gap at the same step."""
+    cannot meet 1e-3: the bound is the reference's OWN bf16-vs-fp32 gap at the same step.
+    Both attention formulations of the bf16 cache: mma.sync over TMA-swizzled tiles (default) and the scalar loop."""
+    monkeypatch.setenv("MVB_PC_ATT_MMA", "1" if attention == "mma" else "0")    # read once in mvb_s1_create
     g = _golden(golden_dir, "stage1_full")
     m = _mk_full(full_arena, "bf16")
     steps = [int(s) for s in g["steps"]]
@@ -367,7 +370,7 @@ def test_persistent_kernel_logits_full_bf16_kv_vs_reference_golden(golden_dir, f
     for i, s in enumerate(steps):
         ref32 = torch.from_numpy(g["logits"][i]); ref16 = torch.from_numpy(g["logits_ref_bf16"][i])
         ours, theirs = _rel(lg[s], ref32), _rel(ref16, ref32)
-        print(f"persistent kernel 1.2B bf16-KV step {s}: engine {ours:.2e} vs reference-bf16 {theirs:.2e}")
+        print(f"persistent kernel 1.2B bf16-KV ({attention} attention) step {s}: engine {ours:.2e} vs reference-bf16 {theirs:.2e}")
         assert ours <= theirs and ours < 1.5e-2
 
 
