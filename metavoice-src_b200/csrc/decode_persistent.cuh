@@ -55,7 +55,7 @@ struct AttTile {
 };
 
 struct PcShared {   // small shared state behind the big buffers
-  uint64_t b_full[8], b_empty[8], b_ready, acc_full[2], acc_empty[2], kv_full[PC_NKV_MAX], kv_empty[PC_NKV_MAX], tab_ready, att_bar;
+  uint64_t b_full[8], b_empty[8], b_ready, acc_full[2], acc_empty[2], kv_full[PC_NKV_MAX], kv_empty[PC_NKV_MAX], tab_ready;
   uint32_t tmem_slot;
   int prod_pos;                      // weight tiles issued so far (producer -> L2 prefetcher)
   int n_att_tiles;
@@ -91,7 +91,7 @@ template <int NB, bool WB> struct PcCfg {
   static constexpr int B_BYTES = PC_BKB_MAX * NB * 128;
   static constexpr int RH = NB / 2;                       // activation rows carried (hi rows; lo rows follow)
   static constexpr int ACC_COLS = WB ? 256 : NB;          // TMEM columns of one accumulator
-  static constexpr int TMEM_COLS = WB ? 512 : 128;        // [0, 2 NB): projection accumulators; [64, 128): attention scores (att_mma = 3)
+  static constexpr int TMEM_COLS = WB ? 512 : 64;
   static constexpr size_t SMEM = 1024 + (size_t)STAGES * STAGE_BYTES + B_BYTES + (size_t)NKV * 2 * PC_KV_TILE_BYTES +
                                  sizeof(PcShared) + 64;
 };
@@ -132,8 +132,7 @@ struct PcParams {
   char* kv;
   size_t kv_half;  // bytes of one layer's K (or V) region
   unsigned* bar;   // grid-wide arrival counter (zero at launch)
-  int att_mma;       // bf16 cache, KV tiles 128B-swizzled through tm_kv: 1 = QK^T and PV on mma.sync; 2 = QK^T on mma.sync, PV one
-                     // thread per output dim; 3 = QK^T on tcgen05 (positions as the N operand), PV one thread per dim; 0 = scalar loop
+  int att_mma;       // 1: bf16 KV tiles arrive 128B-swizzled through tm_kv and the attention runs on mma.sync (see the attention phase)
   long long kv_rows_half;   // cache rows (positions) of one layer's K (or V) region = kv_half / 256
   long long* trace;  // optional [gridDim][PC_TRACE_EVENTS] clock64 stamps of compute-thread 0 (debug)
   S1State st;
@@ -374,7 +373,6 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       ptx::mbar_init(ptx::smem_u32(sh.kv_empty + i), 1);
     }
     ptx::mbar_init(ptx::smem_u32(&sh.tab_ready), 1);
-    ptx::mbar_init(ptx::smem_u32(&sh.att_bar), 1);
     sh.prod_pos = 0;
     ptx::fence_barrier_init();
   }
@@ -607,7 +605,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
     const int ct = tid - 64;            // 0..127
     const int cw = ct >> 5;             // 0..3
     const int quad = warp & 3;          // TMEM lane quadrant this warp may read
-    uint32_t tile_ctr = 0, bar_idx = 0, kv_ctr = 0, att_ctr = 0;
+    uint32_t tile_ctr = 0, bar_idx = 0, kv_ctr = 0;
     const float inv_D = 1.f / (float)p.D;
     pdl_wait();                         // state / x inputs of the previous kernels are visible
     int ev = 0;
@@ -966,9 +964,6 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
           const int g = lane >> 2, t4 = lane & 3, mat = lane >> 3;
           float m = -INFINITY, lsum = 0.f, kcur = 0.f, vcur = 0.f;
           float oacc[2][4];
-          float od = 0.f;                                         // att_mma >= 2: output dim `ct` of this thread
-          float* scl = reinterpret_cast<float*>(qf + 128 + 4 * 64);   // [64] lo-term scores (att_mma = 3), behind the pw regions
-          const int amode = p.att_mma;
           const int n_tiles = sh.n_att_tiles;
 #ifdef PC_ATT_PROF
           long long a_t[5] = {0, 0, 0, 0, 0}, a_c = clock64();   // begin | append cur | kv wait | tile math | cur + unit end
@@ -998,21 +993,9 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
               const float qn = __shfl_down_sync(0xffffffffu, qv, 1);
               qf[ct] = qv;
               if ((ct & 1) == 0) pack_hi_lo(qv, qn, q_hi[ct >> 1], q_lo[ct >> 1]);
-              m = -INFINITY; lsum = 0.f; od = 0.f;
+              m = -INFINITY; lsum = 0.f;
 #pragma unroll
               for (int i = 0; i < 4; ++i) { oacc[0][i] = 0.f; oacc[1][i] = 0.f; }
-              if (amode == 3) {
-                // q as the UMMA A operand: rows 0 (hi) and 1 (lo) of one 128B-swizzled 8-row group per 64-dim half, at the start
-                // of the (idle) activation-operand buffer; rows 2..127 of the M = 128 operand read whatever follows -- their
-                // accumulator lanes are never looked at
-                const __nv_bfloat16 qh = __float2bfloat16_rn(qv);
-                const __nv_bfloat16 ql = __float2bfloat16_rn(qv - __bfloat162float(qh));
-                uint8_t* grp = Bop + (ct >> 6) * 1024;
-                const int c = ct & 63;
-                *reinterpret_cast<__nv_bfloat16*>(grp + ((((c >> 3) ^ 0) << 4) + (c & 7) * 2)) = qh;
-                *reinterpret_cast<__nv_bfloat16*>(grp + 128 + ((((c >> 3) ^ 1) << 4) + (c & 7) * 2)) = ql;
-                fence_async_smem();
-              }
               compute_sync();                                    // q visible to every warp
             }
             PC_ATT_MARK(0)
@@ -1036,40 +1019,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
               PC_ATT_MARK(2)
               const uint32_t kt = ptx::smem_u32(kvbuf + (size_t)ks * 2 * PC_KV_TILE_BYTES);
               const uint32_t vt = kt + PC_KV_TILE_BYTES;
-              if (amode == 3) {
-                // ---- scores on tcgen05: D[128 x 64] = A (q hi / lo in rows 0 / 1) x B (the K tile: 64 positions as N), K = 128
-                if (cw == 0) {
-                  ptx::tc_fence_after();
-                  if (ptx::elect_one()) {
-                    const uint32_t idesc = ptx::umma_idesc_bf16(128, 64);
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                      const uint64_t ad = ptx::umma_desc_k_sw128(ptx::smem_u32(Bop + hf * 1024));
-                      const uint64_t bd = ptx::umma_desc_k_sw128(kt + hf * 8192);
-#pragma unroll
-                      for (int k = 0; k < 4; ++k) ptx::umma_bf16(tmem_base + 64, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((hf | k) != 0));
-                    }
-                    ptx::umma_commit(ptx::smem_u32(&sh.att_bar));
-                  }
-                  __syncwarp();
-                } else if (cw == 2) {                             // warp 4 = TMEM lane quadrant 0: rows 0 and 1 of D
-                  ptx::mbar_wait(ptx::smem_u32(&sh.att_bar), att_ctr & 1u);
-                  ptx::tc_fence_after();
-#pragma unroll
-                  for (int c0 = 0; c0 < 64; c0 += 16) {
-                    uint32_t v[16];
-                    ptx::tmem_ld16(tmem_base + 64 + c0, v);
-                    ptx::tmem_ld_wait();
-                    if (lane < 2) {
-                      float* dst = (lane == 0 ? scv : scl) + c0;
-#pragma unroll
-                      for (int i = 0; i < 16; ++i) dst[i] = __uint_as_float(v[i]);
-                    }
-                  }
-                  ptx::tc_fence_before();
-                }
-                ++att_ctr;
-              } else if (16 * cw < npos) {
+              if (16 * cw < npos) {
                 // ---- scores of positions [16w, 16w+16): A = K rows, B = q (hi, lo) in column 0
                 // four independent accumulator chains (hi / lo terms x even / odd k-steps): the mma latency, not its issue
                 // rate, is what a single warp per scheduler pays
@@ -1099,41 +1049,12 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
               // ---- online softmax over the tile (identical in every warp)
               // tile max with ONE redux.sync on an order-preserving integer image of the floats (a 5-step shuffle butterfly
               // is ~150 cycles of dependent latency); the running sum stays per lane and is reduced once per unit
-              float s0 = scv[lane], s1 = scv[lane + 32];
-              if (amode == 3) {
-                s0 = lane < npos ? s0 + scl[lane] : -INFINITY;
-                s1 = lane + 32 < npos ? s1 + scl[lane + 32] : -INFINITY;
-              }
+              const float s0 = scv[lane], s1 = scv[lane + 32];
               const float mn = fmaxf(m, ordered_to_float(__reduce_max_sync(0xffffffffu, float_to_ordered(fmaxf(s0, s1)))));
               const float mref = (mn == -INFINITY) ? 0.f : mn;
               const float corr = fast_exp(m - mref), p0v = fast_exp(s0 - mref), p1v = fast_exp(s1 - mref);
               lsum = lsum * corr + (p0v + p1v);
               m = mn;
-              if (amode >= 2) {
-                // ---- o[ct] = o[ct] * corr + sum_pos p[pos] V[pos][ct]: one thread per output dim, V read from the swizzled tile
-                float* pf = reinterpret_cast<float*>(pw);          // this warp's copy of the 64 weights
-                pf[lane] = p0v;
-                pf[lane + 32] = p1v;
-                __syncwarp();
-                const uint8_t* vcol = kvbuf + (size_t)ks * 2 * PC_KV_TILE_BYTES + PC_KV_TILE_BYTES + (ct >> 6) * 8192 + (ct & 7) * 2;
-                const int cch = (ct & 63) >> 3;
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                for (int p8 = 0; p8 < npos; p8 += 8) {              // positions >= npos carry weight 0 (finite cache contents)
-#pragma unroll
-                  for (int j = 0; j < 8; j += 4) {
-                    const float v0 = bf16_to_f32(*reinterpret_cast<const __nv_bfloat16*>(vcol + (p8 + j) * 128 + ((cch ^ j) << 4)));
-                    const float v1 = bf16_to_f32(*reinterpret_cast<const __nv_bfloat16*>(vcol + (p8 + j + 1) * 128 + ((cch ^ (j + 1)) << 4)));
-                    const float v2 = bf16_to_f32(*reinterpret_cast<const __nv_bfloat16*>(vcol + (p8 + j + 2) * 128 + ((cch ^ (j + 2)) << 4)));
-                    const float v3 = bf16_to_f32(*reinterpret_cast<const __nv_bfloat16*>(vcol + (p8 + j + 3) * 128 + ((cch ^ (j + 3)) << 4)));
-                    a0 = fmaf(pf[p8 + j], v0, a0);
-                    a1 = fmaf(pf[p8 + j + 1], v1, a1);
-                    a2 = fmaf(pf[p8 + j + 2], v2, a2);
-                    a3 = fmaf(pf[p8 + j + 3], v3, a3);
-                  }
-                }
-                od = fmaf(od, corr, (a0 + a1) + (a2 + a3));
-                __syncwarp();
-              } else {
               {
                 const float n0 = __shfl_down_sync(0xffffffffu, p0v, 1), n1 = __shfl_down_sync(0xffffffffu, p1v, 1);
                 if ((lane & 1) == 0) {
@@ -1168,7 +1089,6 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
               }
 #pragma unroll
               for (int i = 0; i < 4; ++i) { oacc[0][i] += olo[0][i]; oacc[1][i] += olo[1][i]; }
-              }
               PC_ATT_MARK(3)
             }
             if (npos > 0 || has_cur) compute_sync();   // KV tile fully consumed; sh.cur visible
@@ -1181,7 +1101,6 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
               sd = warp_sum(sd);
               const float mn = fmaxf(m, sd), corr = __expf(m - mn), pc = __expf(sd - mn);
               lsum = lsum * corr + (lane == 0 ? pc : 0.f);           // (lsum is a per-lane partial sum)
-              od = od * corr + pc * sh.cur[128 + ct];
 #pragma unroll
               for (int mb = 0; mb < 2; ++mb) {
                 const int d = 32 * cw + 16 * mb + g;
@@ -1193,9 +1112,7 @@ k_decode_persistent(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
             if (unit_last) {
               // every warp holds the same (m, l); output dims live in the lanes with t4 == 0 (column 0 of the C fragments)
               const size_t pidx = ((size_t)r * p.H + h) * PC_MAX_CHUNKS + z;
-              if (amode >= 2) {
-                p.part_o[pidx * 128 + ct] = od;
-              } else if (t4 == 0) {
+              if (t4 == 0) {
 #pragma unroll
                 for (int mb = 0; mb < 2; ++mb) {
                   const int d = 32 * cw + 16 * mb + g;
