@@ -254,6 +254,14 @@ __global__ void k_sched_step(float* __restrict__ cur, const float* __restrict__ 
     cur[i] = v;
   }
 }
+// wav0[t] = sum_m wav_m[t] over the per-model blocks (block stride in floats), in model order
+__global__ void k_sum_blocks(float* __restrict__ wav0, size_t blk_floats, int n, int T) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x) {
+    float a = wav0[i];
+    for (int m = 1; m < n; ++m) a += wav0[(size_t)m * blk_floats + i];
+    wav0[i] = a;
+  }
+}
 __global__ void k_scale_copy(const float* __restrict__ src, float s, float* __restrict__ dst, int T) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x) dst[i] = src[i] * s;
 }
@@ -380,6 +388,10 @@ struct mvb_mbd {
   int per_model = 0;         // tensors per band model
   // tensor-core path (mbd_tc.cuh): packed bf16 taps + their tensor maps, by weight tensor index
   struct TcW { CUtensorMap tmA; int Cin, Cout, K; };
+  char* base = nullptr;      // activation block of the band model whose kernels are being enqueued (host-side cursor)
+  cudaStream_t st[8] = {};   // one stream per band model (n_blk > 1)
+  cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
+  int n_blk = 1;
   std::vector<int> tc_of;    // [n tensors] -> index into tcw, or -1 (CUDA-core path)
   std::vector<TcW> tcw;
   const float* w(int i) const { return reinterpret_cast<const float*>(arena + off[i]); }
@@ -405,7 +417,9 @@ static int mbd_validate(const mvb_mbd_config* c) {
 static int mbd_per_model(const mvb_mbd_config* c) { return c->depth * (3 + 8 * c->res_blocks + 1) + 2 + c->depth * (8 * c->res_blocks + 3) + 2; }
 
 struct MbdWs {
-  size_t cur, est, noise, wav, cond, gn, gn_part, stdv, low, skip[8], tmp[3], xt_hi, xt_lo, wpack, total;
+  size_t cur, est, noise, wav, cond, gn, gn_part, stdv, low, skip[8], tmp[3], xt_hi, xt_lo;   // offsets inside one activation block
+  size_t blk, wpack, total;   // block size; the packed taps follow n_blk blocks (one block per concurrently running band model)
+  int n_blk;
 };
 // Convolutions of one band model in tensor order: fn(tensor index relative to the model, Cin, Cout, K, transposed)
 template <class F>
@@ -436,6 +450,12 @@ static int mbd_tc_cpad(int cin) { return (cin + 63) / 64 * 64; }
 static bool mbd_tc_enabled() {
   const char* e = getenv("MVB_MBD_NO_TC");
   return !(e && e[0] == '1');
+}
+// The band models are independent until their outputs are summed: each runs on its own stream with its own activation
+// block, so the many sub-wave kernels of one UNet (96-CTA convolutions, 4-CTA reductions) overlap with the other models'.
+static bool mbd_streams_enabled() {
+  const char* e = getenv("MVB_MBD_STREAMS");
+  return !(e && e[0] == '0');
 }
 static MbdWs mbd_layout(const mvb_mbd_config* c) {
   MbdWs L{};
@@ -472,8 +492,10 @@ static MbdWs mbd_layout(const mvb_mbd_config* c) {
     mbd_for_each_conv(c, [&](int, int cin, int cout, int k, int) {
       if (mbd_tc_eligible(cin)) wp += ((size_t)k * cout * mbd_tc_cpad(cin) * 2 + 255) / 256 * 256;
     });
-  L.wpack = take(wp * c->n_models + 256);
-  L.total = o;
+  L.blk = (o + 4095) / 4096 * 4096;
+  L.n_blk = (mbd_streams_enabled() && c->n_models > 1) ? c->n_models : 1;
+  L.wpack = L.blk * L.n_blk;
+  L.total = L.wpack + wp * c->n_models + 256;
   return L;
 }
 
@@ -498,6 +520,15 @@ extern "C" int mvb_mbd_create(const mvb_mbd_config* cfg, const void* d_arena, si
   int c = cfg->hidden;
   for (int i = 0; i < cfg->depth; ++i) { h->ch.push_back(c); c = (int)(c * cfg->growth); }
   // tensor-core path: repack the taps of every eligible convolution to bf16 [tap][Cout][Cin] and build their A maps
+  h->n_blk = mbd_layout(cfg).n_blk;
+  h->base = h->ws;
+  if (h->n_blk > 1) {
+    bool ok_s = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < h->n_blk && ok_s; ++i)
+      ok_s = cudaStreamCreateWithFlags(&h->st[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok_s) { mvb_mbd_destroy(h); return mvb::set_error(MVB_ERR_CUDA, "mbd: stream / event creation failed"); }
+  }
   h->tc_of.assign(n_off, -1);
   if (mbd_tc_enabled() && encode_tiled_fn()) {
     const MbdWs L = mbd_layout(cfg);
@@ -528,6 +559,13 @@ extern "C" int mvb_mbd_create(const mvb_mbd_config* cfg, const void* d_arena, si
   return MVB_OK;
 }
 extern "C" int mvb_mbd_destroy(mvb_mbd* h) {
+  if (h) {
+    for (int i = 0; i < 8; ++i) {
+      if (h->st[i]) cudaStreamDestroy(h->st[i]);
+      if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  }
   delete h;
   return MVB_OK;
 }
@@ -542,7 +580,7 @@ static int launch_conv(cudaStream_t s, const ConvP& p, int K, int stride) {
   return MVB_OK;
 }
 static int gn_stats(mvb_mbd* h, cudaStream_t s, const float* x, int C, int T, int groups, float* stats) {
-  double* part = reinterpret_cast<double*>(h->ws + mbd_layout(&h->cfg).gn_part);
+  double* part = reinterpret_cast<double*>(h->base + mbd_layout(&h->cfg).gn_part);
   const size_t n = (size_t)(C / groups) * T;
   k_gn_partial<<<dim3(groups, GN_SPLIT), 256, 0, s>>>(x, n, part);
   k_gn_final<<<groups, 32, 0, s>>>(part, groups, (double)n, 1e-5f, stats);
@@ -555,8 +593,8 @@ static int gn_stats(mvb_mbd* h, cudaStream_t s, const float* x, int C, int T, in
 static int launch_conv_tc(mvb_mbd* h, cudaStream_t s, const ConvP& p, int widx, int kind, int K, int stride) {
   const mvb_mbd::TcW& w = h->tcw[h->tc_of[widx]];
   const MbdWs L = mbd_layout(&h->cfg);
-  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(h->ws + L.xt_hi);
-  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(h->ws + L.xt_lo);
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(h->base + L.xt_hi);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(h->base + L.xt_lo);
   const int Tpad = kind == 1 ? (p.Tin + stride - 1) / stride * stride : p.Tin;
   const int Cp = mbd_tc_cpad(p.Cin);
   k_mbd_prep_t<<<dim3((Tpad + 31) / 32, Cp / 64), 256, 0, s>>>(p.x, p.Cin, Cp, p.Tin, Tpad, p.gn_stats, p.gn_w, p.gn_b,
@@ -614,8 +652,8 @@ static int res_block(mvb_mbd* h, cudaStream_t s, int base, int C, int T, int dil
 static int unet_forward(mvb_mbd* h, cudaStream_t s, int m, int step, const float* cur, int T, const float* d_cond, int Tf, float* est) {
   const mvb_mbd_config& c = h->cfg;
   const MbdWs L = mbd_layout(&c);
-  float* stats = reinterpret_cast<float*>(h->ws + L.gn);
-  float* tmp[3] = {reinterpret_cast<float*>(h->ws + L.tmp[0]), reinterpret_cast<float*>(h->ws + L.tmp[1]), reinterpret_cast<float*>(h->ws + L.tmp[2])};
+  float* stats = reinterpret_cast<float*>(h->base + L.gn);
+  float* tmp[3] = {reinterpret_cast<float*>(h->base + L.tmp[0]), reinterpret_cast<float*>(h->base + L.tmp[1]), reinterpret_cast<float*>(h->base + L.tmp[2])};
   const int pad_k = (c.kernel - c.stride) / 2, G = c.norm_groups;
   int ti = m * h->per_model;
   const float* x = cur;
@@ -634,7 +672,7 @@ static int unet_forward(mvb_mbd* h, cudaStream_t s, int m, int step, const float
     ti += 3;
     float* a = tmp[0];
     float* b = tmp[1];
-    float* skip = reinterpret_cast<float*>(h->ws + L.skip[i]);
+    float* skip = reinterpret_cast<float*>(h->base + L.skip[i]);
     const float* emb = nullptr;
     for (int j = 0; j < c.res_blocks; ++j) {
       const bool last = j == c.res_blocks - 1;
@@ -651,7 +689,7 @@ static int unet_forward(mvb_mbd* h, cudaStream_t s, int m, int step, const float
   const int Cb = h->ch[c.depth - 1];
   float* z = tmp[0];
   {
-    float* cemb = reinterpret_cast<float*>(h->ws + L.cond);
+    float* cemb = reinterpret_cast<float*>(h->base + L.cond);
     ConvP p{};
     p.x = d_cond; p.Cin = c.codec_dim; p.Tin = Tf; p.w = h->w(ti); p.bias = h->w(ti + 1); p.y = cemb; p.Cout = Cb; p.Tout = Tf; p.dil = 1; p.pad = 0;
     if (int e = launch_conv(s, p, 1, 1)) return e;
@@ -666,7 +704,7 @@ static int unet_forward(mvb_mbd* h, cudaStream_t s, int m, int step, const float
   int Tz = Tl, zi = 0;
   for (int i = 0; i < c.depth; ++i) {
     const int lvl = c.depth - 1 - i, C = h->ch[lvl], Tsk = Ts[lvl];
-    const float* skip = reinterpret_cast<const float*>(h->ws + L.skip[lvl]);
+    const float* skip = reinterpret_cast<const float*>(h->base + L.skip[lvl]);
     float* a = tmp[(zi + 1) % 3];
     float* b = tmp[zi];                   // free once the skip sum has been formed
     float* scratch = tmp[(zi + 2) % 3];
@@ -716,10 +754,9 @@ extern "C" int mvb_mbd_tokens_to_wav(mvb_mbd* h, const float* d_cond, int32_t n_
   cudaStream_t s = (cudaStream_t)stream;
   const MbdWs L = mbd_layout(&c);
   const int T = n_samples;
-  float* cur = reinterpret_cast<float*>(h->ws + L.cur);
-  float* est = reinterpret_cast<float*>(h->ws + L.est);
-  float* nz = reinterpret_cast<float*>(h->ws + L.noise);
-  float* wav = reinterpret_cast<float*>(h->ws + L.wav);
+  const bool multi = h->n_blk > 1;
+  h->base = h->ws;
+  float* wav = reinterpret_cast<float*>(h->ws + L.wav);      // block 0: the sum over the band models, then the re-EQ input
   float* low = reinterpret_cast<float*>(h->ws + L.low);
   float* stdv = reinterpret_cast<float*>(h->ws + L.stdv);
   const int g0 = c.n_models * h->per_model;          // globals: processor bank, eq bank, schedule table
@@ -727,31 +764,54 @@ extern "C" int mvb_mbd_tokens_to_wav(mvb_mbd* h, const float* d_cond, int32_t n_
   std::vector<float> hs((size_t)c.n_calls * 4);
   MCK(cudaMemcpyAsync(hs.data(), sched, sizeof(float) * hs.size(), cudaMemcpyDeviceToHost, s));
   MCK(cudaStreamSynchronize(s));
-  MCK(cudaMemsetAsync(wav, 0, sizeof(float) * T, s));
-  for (int m = 0; m < c.n_models; ++m) {
+  if (!multi) MCK(cudaMemsetAsync(wav, 0, sizeof(float) * T, s));
+  if (multi) MCK(cudaEventRecord(h->ev_fork, s));
+  int rc = MVB_OK;
+  for (int m = 0; m < c.n_models && rc == MVB_OK; ++m) {
+    cudaStream_t sm = multi ? h->st[m] : s;
+    h->base = h->ws + (multi ? (size_t)m * L.blk : 0);
+    if (multi) MCK(cudaStreamWaitEvent(sm, h->ev_fork, 0));
+    float* cur = reinterpret_cast<float*>(h->base + L.cur);
+    float* est = reinterpret_cast<float*>(h->base + L.est);
+    float* nz = reinterpret_cast<float*>(h->base + L.noise);
+    float* wav_m = reinterpret_cast<float*>(h->base + L.wav);
+    float* low_m = reinterpret_cast<float*>(h->base + L.low);
     // initial = randn * noise_scale
     const float* n0 = d_noise ? d_noise + ((size_t)m * c.n_calls) * T : nz;
-    if (!d_noise) { k_randn<<<148, 256, 0, s>>>(nz, T, seed, (unsigned)(m * 1024)); MCK(cudaGetLastError()); }
-    k_scale_copy<<<148, 256, 0, s>>>(n0, c.noise_scale, cur, T);
+    if (!d_noise) { k_randn<<<148, 256, 0, sm>>>(nz, T, seed, (unsigned)(m * 1024)); MCK(cudaGetLastError()); }
+    k_scale_copy<<<148, 256, 0, sm>>>(n0, c.noise_scale, cur, T);
     MCK(cudaGetLastError());
     for (int i = 0; i < c.n_calls; ++i) {
       const float a = hs[4 * i], b = hs[4 * i + 1], sigma = hs[4 * i + 2];
       const int step = (int)hs[4 * i + 3];
-      if (int e = unet_forward(h, s, m, step, cur, T, d_cond, n_frames, est)) return e;
+      if ((rc = unet_forward(h, sm, m, step, cur, T, d_cond, n_frames, est)) != MVB_OK) break;
       const float* ni = nullptr;
       if (sigma > 0.f) {
         if (d_noise) ni = d_noise + ((size_t)m * c.n_calls + i + 1) * T;      // row i + 1: the draw added after call i
-        else { k_randn<<<148, 256, 0, s>>>(nz, T, seed, (unsigned)(m * 1024 + i + 1)); MCK(cudaGetLastError()); ni = nz; }
+        else { k_randn<<<148, 256, 0, sm>>>(nz, T, seed, (unsigned)(m * 1024 + i + 1)); MCK(cudaGetLastError()); ni = nz; }
       }
-      k_sched_step<<<148 * 2, 256, 0, s>>>(cur, est, ni, a, b, sigma, c.noise_scale, c.clip, T);
+      k_sched_step<<<148 * 2, 256, 0, sm>>>(cur, est, ni, a, b, sigma, c.noise_scale, c.clip, T);
       MCK(cudaGetLastError());
     }
-    // MultiBandProcessor.return_sample: bands * (std / target_std) ** power_std + mean, summed; accumulate over the band models
+    if (rc != MVB_OK) break;
+    // MultiBandProcessor.return_sample: bands * (std / target_std) ** power_std + mean, summed; the band models' outputs are
+    // added up in model order (one stream: accumulated in place; several streams: per-model buffers summed after the join)
     const int pb = m * h->per_model + h->per_model - 2;
-    if (int e = split_lows(h, s, cur, T, c.proc_bands, h->w(g0), c.proc_taps, low)) return e;
-    k_band_mix<<<148 * 2, 256, 0, s>>>(low, cur, T, c.proc_bands, h->w(pb), nullptr, h->w(pb + 1), wav, 1);
+    if ((rc = split_lows(h, sm, cur, T, c.proc_bands, h->w(g0), c.proc_taps, low_m)) != MVB_OK) break;
+    k_band_mix<<<148 * 2, 256, 0, sm>>>(low_m, cur, T, c.proc_bands, h->w(pb), nullptr, h->w(pb + 1), wav_m, multi ? 0 : 1);
     MCK(cudaGetLastError());
+    if (multi) MCK(cudaEventRecord(h->ev_join[m], sm));
   }
+  h->base = h->ws;
+  if (multi) {
+    // always re-join the caller's stream, also on an error path, so no work is left running behind the caller's back
+    for (int m = 0; m < c.n_models; ++m) MCK(cudaStreamWaitEvent(s, h->ev_join[m], 0));   // (an event never recorded in this call is complete)
+    if (rc == MVB_OK) {
+      k_sum_blocks<<<148 * 2, 256, 0, s>>>(wav, L.blk / 4, c.n_models, T);
+      MCK(cudaGetLastError());
+    }
+  }
+  if (rc != MVB_OK) return rc;
   // re_eq(wav, ref = wav_encodec, eq_bands): out = sum_b band_b(wav) * std(band_b(ref)) / std(band_b(wav))
   float* low_w = low;
   float* low_r = low + (size_t)c.eq_bands * T;
