@@ -2,6 +2,7 @@
 // time, so libmvb200 does not link libcuda) and launch configuration.
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_runtime.h>
 
 #include "umma_gemm.cuh"
@@ -67,6 +68,7 @@ static inline GemmPlan plan_gemm(int M, int K, int NB, bool swiglu, int n_sm) {
   int ks = n_sm / g.tiles;
   if (ks < 1) ks = 1;
   if (ks > nkb / 2) ks = nkb / 2 > 0 ? nkb / 2 : 1;   // at least two k-blocks per split: tiny K is latency-, not bandwidth-bound
+  if (nkb <= 8 && getenv("MVB_GEMM_SPLIT_TINY") == nullptr) ks = 1;   // K <= 512 (stage-2 width): the split-K hand-off costs more than it buys
   if (ks > 16) ks = 16;
   if (g.tiles > 128) ks = 1;                           // (the split-K arrival counters cover 128 tiles)
   g.ksplit = ks;
